@@ -1,0 +1,89 @@
+"""Pin the numpy oracle against fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from aigv_assessor_b200 import synth
+from aigv_assessor_b200.config import VisionPathConfig
+from oracle import preprocess_oracle as po
+from oracle import vit_oracle as vo
+
+
+def _case(golden_dir, golden_meta, name):
+    meta = golden_meta[name]
+    cfg = VisionPathConfig(**meta["cfg"])
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    sd = synth.make_weights(cfg, seed=meta["w_seed"])
+    pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["x_seed"])
+    return cfg, g, sd, pv
+
+
+def test_tiny_tower_matches_reference(golden_dir, golden_meta):
+    cfg, g, sd, pv = _case(golden_dir, golden_meta, "tiny")
+    out, st = vo.extract_feature(pv, sd, cfg, return_stages=True)
+    # fp32 vs fp32: only summation-order noise is allowed
+    assert vo.error_metrics(st["embeddings"][:, ::5], g["embeddings_s"])[0] < 1e-5
+    assert vo.error_metrics(st["layer0"][:, ::5], g["layer0_s"])[0] < 1e-5
+    assert vo.error_metrics(st["layer1"], g["vit_out"])[0] < 1e-5
+    assert out.shape == (2, 256, cfg.llm_hidden)
+    assert vo.error_metrics(out, g["out"])[0] < 1e-5
+
+
+def test_tiny_rms_qknorm_tower_matches_reference(golden_dir, golden_meta):
+    cfg, g, sd, pv = _case(golden_dir, golden_meta, "tiny_rms")
+    assert cfg.norm_type == "rms_norm" and cfg.qk_normalization and not cfg.qkv_bias
+    out, st = vo.extract_feature(pv, sd, cfg, return_stages=True)
+    assert vo.error_metrics(st["embeddings"][:, ::41, ::16], g["embeddings_s"])[0] < 1e-5
+    assert vo.error_metrics(st["layer1"][:, ::41, ::16], g["vit_out_s"])[0] < 1e-5
+    assert vo.error_metrics(out[:, ::8, ::16], g["out_s"])[0] < 1e-5
+
+
+@pytest.mark.slow
+def test_vit300m_one_frame_matches_reference(golden_dir, golden_meta):
+    cfg, g, sd, pv = _case(golden_dir, golden_meta, "vit300m")
+    out, st = vo.extract_feature(pv, sd, cfg, return_stages=True)
+    assert vo.error_metrics(st["layer0"][:, ::41, ::16], g["layer0_s"])[0] < 1e-5
+    assert vo.error_metrics(st["layer23"][:, ::41, ::16], g["vit_out_s"])[0] < 2e-5
+    assert vo.error_metrics(out[:, ::8, ::16], g["out_s"])[0] < 2e-5
+    assert abs(np.abs(out).max() - golden_meta["vit300m"]["out_absmax"]) < 1e-4
+
+
+def test_pixel_shuffle_index_law():
+    # out[n,I,J,(2di+dj)C+c] = in[n,2I+di,2J+dj,c] for ps_version v2
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 8, 8, 5)).astype(np.float32)
+    y = vo.pixel_shuffle(x, 0.5, "v2")
+    assert y.shape == (2, 4, 4, 20)
+    for (I, J, di, dj, c) in [(0, 0, 0, 0, 0), (1, 2, 1, 0, 3), (3, 3, 1, 1, 4), (2, 0, 0, 1, 2)]:
+        assert np.array_equal(y[:, I, J, (2 * di + dj) * 5 + c], x[:, 2 * I + di, 2 * J + dj, c])
+
+
+def test_preprocess_matches_reference(golden_meta):
+    for case in golden_meta["preprocess"]["cases"]:
+        frame = synth.make_frames(1, case["h"], case["w"], seed=case["seed"], kind=case["kind"])
+        tiles, pv, counts = po.load_video_frames(frame, max_num=case["max_num"], use_thumbnail=True)
+        assert counts == [case["n_tiles"]]
+        assert hashlib.sha256(tiles.tobytes()).hexdigest() == case["tiles_sha256"], case
+        assert tiles[0, 100:104, 200:204].tolist() == case["tile0_crop"]
+        assert hashlib.sha256(np.ascontiguousarray(pv).tobytes()).hexdigest() == case["pv_sha256"], case
+        assert hashlib.sha256(synth.to_bf16_bits(pv).tobytes()).hexdigest() == case["pv_bf16_sha256"]
+
+
+def test_resize_matches_installed_pillow():
+    from PIL import Image
+    for (h, w, ow, oh, kind) in [(720, 1280, 448, 448, "uniform"), (300, 200, 896, 448, "smooth"),
+                                 (512, 768, 1344, 896, "uniform"), (449, 447, 448, 448, "uniform")]:
+        f = synth.make_frames(1, h, w, seed=7, kind=kind)[0]
+        a = po.resize_bicubic_u8(f, ow, oh)
+        b = np.asarray(Image.fromarray(f).resize((ow, oh)))
+        assert np.array_equal(a, b), (h, w, ow, oh)
+
+
+def test_normalize_lut_is_the_transform():
+    lut = synth.normalize_lut()
+    tile = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, axis=2)
+    pv = po.transform(tile)
+    for c in range(3):
+        assert np.array_equal(pv[c, 0], lut[c])
