@@ -1,0 +1,15 @@
+"""aigv_assessor_b200 — B200-native (sm_100a) vision hot path of AIGV-Assessor behind the reference's
+``extract_feature`` seam. See DESIGN.md / INTEGRATION.md."""
+from .config import VisionPathConfig, internvit_300m, internvit_6b, tiny  # noqa: F401
+
+__all__ = ["VisionPathConfig", "internvit_300m", "internvit_6b", "tiny", "VisionEngine", "install", "uninstall"]
+
+
+def __getattr__(name):  # torch-dependent pieces are imported lazily so config/synth stay importable anywhere
+    if name == "VisionEngine":
+        from .engine import VisionEngine
+        return VisionEngine
+    if name in ("install", "uninstall"):
+        from . import plugin
+        return getattr(plugin, name)
+    raise AttributeError(name)

@@ -1,0 +1,133 @@
+"""Build and load ``libaigv_b200.so`` (the C-ABI of include/aigv_b200.h) with ctypes.
+
+The library is built IN-TREE next to this file (``nvcc -shared``, sm_100a only) so it travels with the repo snapshot;
+there is no JIT cache and no CPU fallback: if the library is missing or does not load, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libaigv_b200.so")
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "rowops.cu", "preprocess.cu"]
+HEADERS = ["kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "aigv_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class AigvError(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise AigvError("nvcc not found; cannot build libaigv_b200.so")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into libaigv_b200.so (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise AigvError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class Cfg(C.Structure):
+    _fields_ = [("hidden_size", C.c_int32), ("num_heads", C.c_int32), ("intermediate_size", C.c_int32),
+                ("num_layers", C.c_int32), ("image_size", C.c_int32), ("patch_size", C.c_int32),
+                ("llm_hidden", C.c_int32), ("qkv_bias", C.c_int32), ("qk_normalization", C.c_int32),
+                ("norm_type", C.c_int32), ("layer_norm_eps", C.c_float), ("mlp1_ln_eps", C.c_float),
+                ("max_tiles", C.c_int32)]
+
+
+# name -> (restype, argtypes): exactly the symbols include/aigv_b200.h declares
+_P = C.c_void_p
+_F = C.POINTER(C.c_float)
+SIGNATURES = {
+    "aigv_version": (C.c_char_p, []),
+    "aigv_status_string": (C.c_char_p, [C.c_int]),
+    "aigv_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(_P)]),
+    "aigv_destroy": (None, [_P]),
+    "aigv_last_error": (C.c_char_p, [_P]),
+    "aigv_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
+    "aigv_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "aigv_finalize_weights": (C.c_int, [_P, _P]),
+    "aigv_extract_feature": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "aigv_copy_vit_hidden": (C.c_int, [_P, _P, C.c_int, _P]),
+    "aigv_profile_enable": (C.c_int, [_P, C.c_int]),
+    "aigv_profile_num_classes": (C.c_int, []),
+    "aigv_profile_class_name": (C.c_char_p, [C.c_int]),
+    "aigv_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "aigv_launch_count": (C.c_int64, [_P]),
+    "aigv_tile_grid": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "aigv_preprocess_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                     C.c_int, _P, _P, _P]),
+    "aigv_gemm_epilogue": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "aigv_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "aigv_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
+    "aigv_rmsnorm_inplace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "aigv_im2col": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "aigv_assemble_tokens": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "aigv_pixel_shuffle": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
+}
+
+_lib = None
+
+
+def load(build_if_missing: bool = True):
+    """dlopen the library and bind every declared symbol. Raises AigvError when it cannot (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise AigvError(f"{LIB_PATH} is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        build()
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise AigvError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise AigvError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, handle=None, what: str = ""):
+    if status == 0:
+        return
+    lib = load()
+    msg = lib.aigv_status_string(status).decode()
+    if handle:
+        detail = lib.aigv_last_error(handle)
+        if detail:
+            msg += ": " + detail.decode()
+    if status in (-1, -4, -5):
+        raise ValueError(f"{what}: {msg}" if what else msg)
+    raise AigvError(f"{what}: {msg}" if what else msg)

@@ -1,0 +1,785 @@
+// C-ABI layer (include/aigv_b200.h): handle, weight ingestion/re-packing, the fused extract_feature schedule,
+// the frame front end and per-op test entry points. No torch types; nothing throws across the boundary.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/aigv_b200.h"
+#include "kernels.h"
+
+namespace aigv {
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                      uint32_t box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return -1;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0 || box_cols * 2 != 128 || box_rows > 256)
+        return -2;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estride[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+static int device_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// ------------------------------------------------------------------------------------------------ dtype conversion
+__global__ void cvt_f32_to_bf16_kernel(const float* s, __nv_bfloat16* d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void cvt_bf16_to_f32_kernel(const __nv_bfloat16* s, float* d, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        d[i] = __bfloat162float(s[i]);
+}
+// [rows, kreal] (any dtype already converted to bf16) -> [rows, kpad] zero padded
+__global__ void pad_rows_bf16_kernel(const __nv_bfloat16* s, __nv_bfloat16* d, int rows, int kreal, int kpad) {
+    const size_t n = (size_t)rows * kpad;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % kpad);
+        const size_t r = i / kpad;
+        d[i] = k < kreal ? s[r * kreal + k] : __float2bfloat16_rn(0.f);
+    }
+}
+
+}  // namespace aigv
+
+using namespace aigv;
+
+// ------------------------------------------------------------------------------------------------ handle
+namespace {
+
+struct Slot {
+    void* dst = nullptr;     // device destination
+    size_t count = 0;        // elements expected from the caller
+    bool as_bf16 = false;    // matrices are kept bf16 (tensor-core operands); vectors fp32
+    int pad_rows = 0;        // patch-embedding weight: rows to zero-pad from pad_kreal to pad_kpad columns
+    int pad_kreal = 0, pad_kpad = 0;
+    bool set = false;
+    bool required = true;
+};
+
+struct LayerW {
+    __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+    float *qkv_b, *proj_b, *fc1_b, *fc2_b, *ls1, *ls2, *n1w, *n1b, *n2w, *n2b, *qnw, *knw;
+    CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
+};
+
+struct ActMaps {
+    int n = -1;
+    CUtensorMap patches, xn, attn, h, ps, m1, qkv_full, qkv_tail;
+};
+
+enum KClass { K_IM2COL = 0, K_GEMM_PATCH, K_ASSEMBLE, K_NORM, K_GEMM_QKV, K_QKNORM, K_ATTENTION, K_GEMM_PROJ,
+              K_GEMM_FC1, K_GEMM_FC2, K_PIXEL_SHUFFLE_LN, K_GEMM_MLP1_A, K_GEMM_MLP1_B, K_PREPROCESS, K_NUM };
+const char* const kClassNames[K_NUM] = {"im2col", "gemm_patch_embed", "assemble_tokens", "norm", "gemm_qkv", "qk_norm",
+                                        "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "pixel_shuffle_ln",
+                                        "gemm_mlp1_a", "gemm_mlp1_b", "preprocess"};
+struct ProfRec { int cls; cudaEvent_t a, b; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRec> pool;   // reusable event pairs
+    size_t used = 0;
+    double ms[K_NUM] = {0};
+    int64_t cnt[K_NUM] = {0};
+};
+
+struct PlanDev {
+    int32_t *kx = nullptr, *bx = nullptr, *ky = nullptr, *by = nullptr;
+    int ksize_x = 0, ksize_y = 0, max_rows = 0;
+};
+
+}  // namespace
+
+struct aigv_handle {
+    aigv_cfg cfg{};
+    int D = 0, H = 0, hd = 0, I = 0, L = 0, C = 0, S = 0, P = 0, g = 0, kreal = 0, kpad = 0, W4 = 0, T = 0;
+    int num_sms = 148;
+    bool finalized = false;
+    std::string err;
+    std::vector<void*> allocs;
+    std::unordered_map<std::string, Slot> slots;
+    std::vector<LayerW> layers;
+    __nv_bfloat16 *pe_w = nullptr, *m1_w = nullptr, *m2_w = nullptr;
+    float *pe_b = nullptr, *cls = nullptr, *pos = nullptr, *mln_w = nullptr, *mln_b = nullptr, *m1_b = nullptr,
+          *m2_b = nullptr;
+    CUtensorMap tm_pe_w, tm_m1_w, tm_m2_w;
+    // workspace (sized for cfg.max_tiles)
+    int max_tiles = 0;
+    size_t ws_bytes = 0;
+    float *x = nullptr, *pe = nullptr;
+    __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *patches = nullptr, *ps = nullptr,
+                  *m1 = nullptr;
+    ActMaps maps;
+    // front end
+    float* lut = nullptr;
+    std::map<std::tuple<int, int, int, int>, PlanDev> plans;
+    // instrumentation
+    Profiler prof;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(aigv_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+int cuda_fail(aigv_handle* h, cudaError_t e, const char* what) {
+    return fail(h, AIGV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <typename T>
+bool dev_alloc(aigv_handle* h, T** p, size_t count, bool zero = false) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(&q, bytes) != cudaSuccess) return false;
+    if (zero) cudaMemset(q, 0, bytes);
+    h->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return true;
+}
+
+void add_slot(aigv_handle* h, const std::string& name, void* dst, size_t count, bool as_bf16, bool required = true) {
+    Slot s;
+    s.dst = dst;
+    s.count = count;
+    s.as_bf16 = as_bf16;
+    s.required = required;
+    h->slots[name] = s;
+}
+
+size_t workspace_bytes_for(const aigv_handle* h, int t) {
+    const size_t M = (size_t)t * h->S, Mp = (size_t)t * h->P, Mo = (size_t)t * (h->g / 2) * (h->g / 2);
+    size_t b = 0;
+    b += M * h->D * 4;        // x
+    b += Mp * h->D * 4;       // pe
+    b += M * h->D * 2;        // xn
+    b += M * 3 * h->D * 2;    // qkv
+    b += M * h->D * 2;        // attn
+    b += M * h->I * 2;        // h
+    b += Mp * h->kpad * 2;    // patches
+    b += Mo * h->W4 * 2;      // ps
+    b += Mo * h->C * 2;       // m1
+    return b;
+}
+
+int build_act_maps(aigv_handle* h, int n) {
+    if (h->maps.n == n) return 0;
+    const uint64_t M = (uint64_t)n * h->S, Mp = (uint64_t)n * h->P, Mo = (uint64_t)n * (h->g / 2) * (h->g / 2);
+    const int ba = gemm_box_rows_a(), bc = gemm_box_cols();
+    int r = 0;
+    r |= make_tmap_bf16_2d(&h->maps.patches, h->patches, Mp, h->kpad, h->kpad, ba, bc);
+    r |= make_tmap_bf16_2d(&h->maps.xn, h->xn, M, h->D, h->D, ba, bc);
+    r |= make_tmap_bf16_2d(&h->maps.attn, h->attn, M, h->D, h->D, ba, bc);
+    r |= make_tmap_bf16_2d(&h->maps.h, h->hbuf, M, h->I, h->I, ba, bc);
+    r |= make_tmap_bf16_2d(&h->maps.ps, h->ps, Mo, h->W4, h->W4, ba, bc);
+    r |= make_tmap_bf16_2d(&h->maps.m1, h->m1, Mo, h->C, h->C, ba, bc);
+    r |= make_tmap_bf16_2d(&h->maps.qkv_full, h->qkv, M, 3 * h->D, 3 * h->D, 128, 64);
+    r |= make_tmap_bf16_2d(&h->maps.qkv_tail, h->qkv, M, 3 * h->D, 3 * h->D, attention_tail_rows(h->S), 64);
+    if (r) return -1;
+    h->maps.n = n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* aigv_version(void) { return "aigv_b200 0.1 (sm_100a tcgen05/TMA)"; }
+
+const char* aigv_status_string(int s) {
+    switch (s) {
+        case AIGV_OK: return "ok";
+        case AIGV_ERR_INVALID: return "invalid argument";
+        case AIGV_ERR_CUDA: return "CUDA error";
+        case AIGV_ERR_MISSING: return "missing weight";
+        case AIGV_ERR_STATE: return "bad call order";
+        case AIGV_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown";
+    }
+}
+
+const char* aigv_last_error(const aigv_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+size_t aigv_workspace_bytes(const aigv_handle* h, int n_tiles) {
+    if (!h || n_tiles <= 0) return 0;
+    return workspace_bytes_for(h, n_tiles < h->max_tiles ? n_tiles : h->max_tiles);
+}
+
+void aigv_destroy(aigv_handle* h) {
+    if (!h) return;
+    for (auto& r : h->prof.pool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
+    if (!cfg || !out) return AIGV_ERR_INVALID;
+    *out = nullptr;
+    aigv_handle* h = nullptr;
+    try {
+        h = new aigv_handle();
+    } catch (...) {
+        return AIGV_ERR_INVALID;
+    }
+    h->cfg = *cfg;
+    h->D = cfg->hidden_size; h->H = cfg->num_heads; h->I = cfg->intermediate_size; h->L = cfg->num_layers;
+    h->C = cfg->llm_hidden; h->P = 0;
+    auto bad = [&](int code, const char* msg) {
+        // keep the handle alive so the caller can read the message, but hand back the code
+        h->err = msg;
+        *out = h;
+        return code;
+    };
+    if (h->D <= 0 || h->H <= 0 || h->I <= 0 || h->L <= 0 || h->C <= 0 || cfg->patch_size <= 0 ||
+        cfg->image_size <= 0 || cfg->max_tiles <= 0)
+        return bad(AIGV_ERR_INVALID, "non-positive dimension in aigv_cfg");
+    if (h->D % h->H) return bad(AIGV_ERR_INVALID, "hidden_size not divisible by num_heads");
+    h->hd = h->D / h->H;
+    if (cfg->image_size % cfg->patch_size) return bad(AIGV_ERR_INVALID, "image_size not divisible by patch_size");
+    h->g = cfg->image_size / cfg->patch_size;
+    h->P = h->g * h->g;
+    h->S = h->P + 1;
+    h->kreal = 3 * cfg->patch_size * cfg->patch_size;
+    h->kpad = ((h->kreal + 63) / 64) * 64;
+    h->W4 = 4 * h->D;
+    h->T = (h->g / 2) * (h->g / 2);
+    if (h->hd != 64) return bad(AIGV_ERR_UNSUPPORTED, "attention kernel covers head_dim 64 only (InternViT-300M)");
+    if (h->g % 2) return bad(AIGV_ERR_UNSUPPORTED, "patch grid must be even for the 2x2 pixel shuffle");
+    if (h->D % 32 || h->I % 32 || h->C % 32 || cfg->patch_size % 2)
+        return bad(AIGV_ERR_UNSUPPORTED, "hidden/intermediate/llm widths must be multiples of 32");
+    h->num_sms = device_num_sms();
+    h->max_tiles = cfg->max_tiles;
+
+    const size_t D = h->D, I = h->I, C = h->C;
+    bool ok = true;
+    ok &= dev_alloc(h, &h->pe_w, D * h->kpad, true);
+    ok &= dev_alloc(h, &h->pe_b, D);
+    ok &= dev_alloc(h, &h->cls, D);
+    ok &= dev_alloc(h, &h->pos, (size_t)h->S * D);
+    ok &= dev_alloc(h, &h->mln_w, (size_t)h->W4);
+    ok &= dev_alloc(h, &h->mln_b, (size_t)h->W4);
+    ok &= dev_alloc(h, &h->m1_w, C * h->W4);
+    ok &= dev_alloc(h, &h->m1_b, C);
+    ok &= dev_alloc(h, &h->m2_w, C * C);
+    ok &= dev_alloc(h, &h->m2_b, C);
+    const std::string pre = "vision_model.";
+    if (ok) {
+        add_slot(h, pre + "embeddings.class_embedding", h->cls, D, false);
+        add_slot(h, pre + "embeddings.position_embedding", h->pos, (size_t)h->S * D, false);
+        add_slot(h, pre + "embeddings.patch_embedding.weight", h->pe_w, D * h->kreal, true);
+        Slot& s = h->slots[pre + "embeddings.patch_embedding.weight"];
+        s.pad_rows = h->D; s.pad_kreal = h->kreal; s.pad_kpad = h->kpad;
+        add_slot(h, pre + "embeddings.patch_embedding.bias", h->pe_b, D, false);
+        add_slot(h, "mlp1.0.weight", h->mln_w, h->W4, false);
+        add_slot(h, "mlp1.0.bias", h->mln_b, h->W4, false);
+        add_slot(h, "mlp1.1.weight", h->m1_w, C * h->W4, true);
+        add_slot(h, "mlp1.1.bias", h->m1_b, C, false);
+        add_slot(h, "mlp1.3.weight", h->m2_w, C * C, true);
+        add_slot(h, "mlp1.3.bias", h->m2_b, C, false);
+    }
+    h->layers.resize(h->L);
+    const bool ln = cfg->norm_type == AIGV_LAYER_NORM;
+    for (int l = 0; ok && l < h->L; ++l) {
+        LayerW& w = h->layers[l];
+        memset(&w, 0, sizeof(w));
+        ok &= dev_alloc(h, &w.qkv_w, 3 * D * D);
+        ok &= dev_alloc(h, &w.proj_w, D * D);
+        ok &= dev_alloc(h, &w.fc1_w, I * D);
+        ok &= dev_alloc(h, &w.fc2_w, D * I);
+        ok &= dev_alloc(h, &w.qkv_b, 3 * D, true);
+        ok &= dev_alloc(h, &w.proj_b, D);
+        ok &= dev_alloc(h, &w.fc1_b, I);
+        ok &= dev_alloc(h, &w.fc2_b, D);
+        ok &= dev_alloc(h, &w.ls1, D);
+        ok &= dev_alloc(h, &w.ls2, D);
+        ok &= dev_alloc(h, &w.n1w, D);
+        ok &= dev_alloc(h, &w.n2w, D);
+        ok &= dev_alloc(h, &w.n1b, D, true);
+        ok &= dev_alloc(h, &w.n2b, D, true);
+        ok &= dev_alloc(h, &w.qnw, D);
+        ok &= dev_alloc(h, &w.knw, D);
+        if (!ok) break;
+        const std::string lp = pre + "encoder.layers." + std::to_string(l) + ".";
+        add_slot(h, lp + "ls1", w.ls1, D, false);
+        add_slot(h, lp + "ls2", w.ls2, D, false);
+        add_slot(h, lp + "attn.qkv.weight", w.qkv_w, 3 * D * D, true);
+        if (cfg->qkv_bias) add_slot(h, lp + "attn.qkv.bias", w.qkv_b, 3 * D, false);
+        if (cfg->qk_normalization) {
+            add_slot(h, lp + "attn.q_norm.weight", w.qnw, D, false);
+            add_slot(h, lp + "attn.k_norm.weight", w.knw, D, false);
+        }
+        add_slot(h, lp + "attn.proj.weight", w.proj_w, D * D, true);
+        add_slot(h, lp + "attn.proj.bias", w.proj_b, D, false);
+        add_slot(h, lp + "mlp.fc1.weight", w.fc1_w, I * D, true);
+        add_slot(h, lp + "mlp.fc1.bias", w.fc1_b, I, false);
+        add_slot(h, lp + "mlp.fc2.weight", w.fc2_w, D * I, true);
+        add_slot(h, lp + "mlp.fc2.bias", w.fc2_b, D, false);
+        add_slot(h, lp + "norm1.weight", w.n1w, D, false);
+        add_slot(h, lp + "norm2.weight", w.n2w, D, false);
+        if (ln) {
+            add_slot(h, lp + "norm1.bias", w.n1b, D, false);
+            add_slot(h, lp + "norm2.bias", w.n2b, D, false);
+        }
+    }
+    // workspace
+    const size_t M = (size_t)h->max_tiles * h->S, Mp = (size_t)h->max_tiles * h->P, Mo = (size_t)h->max_tiles * h->T;
+    if (ok) {
+        ok &= dev_alloc(h, &h->x, M * D, true);
+        ok &= dev_alloc(h, &h->pe, Mp * D, true);
+        ok &= dev_alloc(h, &h->xn, M * D, true);
+        ok &= dev_alloc(h, &h->qkv, M * 3 * D, true);
+        ok &= dev_alloc(h, &h->attn, M * D, true);
+        ok &= dev_alloc(h, &h->hbuf, M * I, true);
+        ok &= dev_alloc(h, &h->patches, Mp * h->kpad, true);
+        ok &= dev_alloc(h, &h->ps, Mo * h->W4, true);
+        ok &= dev_alloc(h, &h->m1, Mo * C, true);
+        h->ws_bytes = workspace_bytes_for(h, h->max_tiles);
+    }
+    // front-end normalisation table: ((u/255) - mean)/std in fp32, as torchvision ToTensor + Normalize
+    if (ok) ok &= dev_alloc(h, &h->lut, 768);
+    if (ok) {
+        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+        float lut[768];
+        for (int c = 0; c < 3; ++c)
+            for (int u = 0; u < 256; ++u) {
+                volatile float t = (float)u / 255.0f;
+                volatile float d = t - mean[c];
+                lut[c * 256 + u] = d / stdv[c];
+            }
+        ok &= cudaMemcpy(h->lut, lut, sizeof(lut), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaError_t e = cudaGetLastError();
+        std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
+        for (void* p : h->allocs) cudaFree(p);
+        h->allocs.clear();
+        h->err = msg;
+        *out = h;
+        return AIGV_ERR_CUDA;
+    }
+    *out = h;
+    return AIGV_OK;
+}
+
+int aigv_set_weight(aigv_handle* h, const char* name, const void* ptr, int dtype, const int64_t* shape, int rank) {
+    if (!h || !name || !ptr || !shape || rank <= 0) return fail(h, AIGV_ERR_INVALID, "aigv_set_weight: null argument");
+    if (dtype != AIGV_F32 && dtype != AIGV_BF16) return fail(h, AIGV_ERR_INVALID, "aigv_set_weight: dtype");
+    std::string key(name);
+    auto it = h->slots.find(key);
+    if (it == h->slots.end()) {
+        it = h->slots.find("vision_model." + key);
+        if (it == h->slots.end()) return fail(h, AIGV_ERR_INVALID, "unknown weight name: " + key);
+    }
+    Slot& s = it->second;
+    size_t count = 1;
+    for (int i = 0; i < rank; ++i) count *= (size_t)shape[i];
+    if (count != s.count)
+        return fail(h, AIGV_ERR_INVALID, "shape mismatch for " + key + ": got " + std::to_string(count) +
+                                             " elements, expected " + std::to_string(s.count));
+    const size_t esz = dtype == AIGV_F32 ? 4 : 2;
+    void* stage = nullptr;
+    cudaError_t e = cudaMalloc(&stage, count * esz);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc(stage)");
+    e = cudaMemcpy(stage, ptr, count * esz, cudaMemcpyDefault);
+    if (e != cudaSuccess) { cudaFree(stage); return cuda_fail(h, e, "cudaMemcpy(weight)"); }
+    const int blocks = 1024, threads = 256;
+    void* conv = nullptr;  // converted, unpadded
+    if (s.as_bf16) {
+        if (dtype == AIGV_BF16) conv = stage;
+        else {
+            e = cudaMalloc(&conv, count * 2);
+            if (e != cudaSuccess) { cudaFree(stage); return cuda_fail(h, e, "cudaMalloc(conv)"); }
+            cvt_f32_to_bf16_kernel<<<blocks, threads>>>((const float*)stage, (__nv_bfloat16*)conv, count);
+        }
+        if (s.pad_rows)
+            pad_rows_bf16_kernel<<<blocks, threads>>>((const __nv_bfloat16*)conv, (__nv_bfloat16*)s.dst, s.pad_rows,
+                                                      s.pad_kreal, s.pad_kpad);
+        else
+            cudaMemcpy(s.dst, conv, count * 2, cudaMemcpyDeviceToDevice);
+    } else {
+        if (dtype == AIGV_F32) cudaMemcpy(s.dst, stage, count * 4, cudaMemcpyDeviceToDevice);
+        else cvt_bf16_to_f32_kernel<<<blocks, threads>>>((const __nv_bfloat16*)stage, (float*)s.dst, count);
+    }
+    e = cudaDeviceSynchronize();
+    if (conv && conv != stage) cudaFree(conv);
+    cudaFree(stage);
+    if (e != cudaSuccess) return cuda_fail(h, e, "weight conversion");
+    s.set = true;
+    h->finalized = false;
+    return AIGV_OK;
+}
+
+int aigv_finalize_weights(aigv_handle* h, void* stream) {
+    (void)stream;
+    if (!h) return AIGV_ERR_INVALID;
+    for (auto& kv : h->slots)
+        if (kv.second.required && !kv.second.set) return fail(h, AIGV_ERR_MISSING, "weight not set: " + kv.first);
+    const int bb = gemm_box_rows_b(), bc = gemm_box_cols();
+    int r = 0;
+    r |= make_tmap_bf16_2d(&h->tm_pe_w, h->pe_w, h->D, h->kpad, h->kpad, bb, bc);
+    r |= make_tmap_bf16_2d(&h->tm_m1_w, h->m1_w, h->C, h->W4, h->W4, bb, bc);
+    r |= make_tmap_bf16_2d(&h->tm_m2_w, h->m2_w, h->C, h->C, h->C, bb, bc);
+    for (auto& w : h->layers) {
+        r |= make_tmap_bf16_2d(&w.tm_qkv, w.qkv_w, 3 * h->D, h->D, h->D, bb, bc);
+        r |= make_tmap_bf16_2d(&w.tm_proj, w.proj_w, h->D, h->D, h->D, bb, bc);
+        r |= make_tmap_bf16_2d(&w.tm_fc1, w.fc1_w, h->I, h->D, h->D, bb, bc);
+        r |= make_tmap_bf16_2d(&w.tm_fc2, w.fc2_w, h->D, h->I, h->I, bb, bc);
+    }
+    if (r) return fail(h, AIGV_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix");
+    h->finalized = true;
+    return AIGV_OK;
+}
+
+#define AIGV_TRY(expr, what)                                   \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return cuda_fail(h, _e, what);  \
+    } while (0)
+
+namespace {
+// Optional per-launch CUDA-event bracket on the launching stream (bench.py's live roofline numbers).
+struct ProfScope {
+    aigv_handle* h;
+    cudaStream_t st;
+    ProfRec* rec = nullptr;
+    ProfScope(aigv_handle* h_, int cls, cudaStream_t st_) : h(h_), st(st_) {
+        h->launches++;
+        if (!h->prof.on) return;
+        Profiler& p = h->prof;
+        if (p.used == p.pool.size()) {
+            ProfRec r{cls, nullptr, nullptr};
+            if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+            p.pool.push_back(r);
+        }
+        rec = &p.pool[p.used++];
+        rec->cls = cls;
+        cudaEventRecord(rec->a, st);
+    }
+    ~ProfScope() {
+        if (rec) cudaEventRecord(rec->b, st);
+    }
+};
+}  // namespace
+
+#define AIGV_LAUNCH(cls, expr, what)                           \
+    do {                                                       \
+        ProfScope _ps(h, cls, st);                             \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return cuda_fail(h, _e, what);  \
+    } while (0)
+
+static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bfloat16* out, cudaStream_t st) {
+    if (build_act_maps(h, n)) return fail(h, AIGV_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation matrix");
+    const int D = h->D, I = h->I, C = h->C, S = h->S;
+    const int M = n * S, Mp = n * h->P, Mo = n * h->T;
+    const bool rms = h->cfg.norm_type == AIGV_RMS_NORM;
+    const float eps = h->cfg.layer_norm_eps;
+    const float scale = 1.0f / sqrtf((float)h->hd);
+
+    // V1: patch embedding = im2col + GEMM(+bias) ; cls + position embedding
+    AIGV_LAUNCH(K_IM2COL, launch_im2col(pv, h->patches, n, h->cfg.image_size, h->cfg.patch_size, h->kpad, st), "im2col");
+    {
+        GemmEpilogue ep;
+        ep.bias = h->pe_b; ep.out_f32 = h->pe; ep.ld_out = D;
+        AIGV_LAUNCH(K_GEMM_PATCH, launch_gemm(h->maps.patches, h->tm_pe_w, Mp, D, h->kpad, ep, h->num_sms, st), "patch-embed gemm");
+    }
+    AIGV_LAUNCH(K_ASSEMBLE, launch_assemble_tokens(h->pe, h->cls, h->pos, h->x, n, h->P, D, st), "assemble tokens");
+
+    for (int l = 0; l < h->L; ++l) {
+        LayerW& w = h->layers[l];
+        // V2 norm1 -> V3 qkv -> (V3b qk-norm) -> V4 attention -> V5 proj * ls1 + residual
+        AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n1w, rms ? nullptr : w.n1b, h->xn, M, D, eps, rms, st), "norm1");
+        {
+            GemmEpilogue ep;
+            ep.bias = h->cfg.qkv_bias ? w.qkv_b : nullptr; ep.out_bf16 = h->qkv; ep.ld_out = 3 * D;
+            AIGV_LAUNCH(K_GEMM_QKV, launch_gemm(h->maps.xn, w.tm_qkv, M, 3 * D, D, ep, h->num_sms, st), "qkv gemm");
+        }
+        if (h->cfg.qk_normalization) {
+            AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st), "q_norm");
+            AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.knw, M, D, 3 * D, D, eps, st), "k_norm");
+        }
+        AIGV_LAUNCH(K_ATTENTION, launch_attention(h->maps.qkv_full, h->maps.qkv_tail, h->attn, n, S, h->H, h->hd, scale, st),
+                 "attention");
+        {
+            GemmEpilogue ep;
+            ep.bias = w.proj_b; ep.colscale = w.ls1; ep.residual = h->x; ep.ld_res = D; ep.out_f32 = h->x; ep.ld_out = D;
+            AIGV_LAUNCH(K_GEMM_PROJ, launch_gemm(h->maps.attn, w.tm_proj, M, D, D, ep, h->num_sms, st), "proj gemm");
+        }
+        // V2 norm2 -> V6 fc1+GELU -> V7 fc2 * ls2 + residual
+        AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n2w, rms ? nullptr : w.n2b, h->xn, M, D, eps, rms, st), "norm2");
+        {
+            GemmEpilogue ep;
+            ep.bias = w.fc1_b; ep.gelu = 1; ep.out_bf16 = h->hbuf; ep.ld_out = I;
+            AIGV_LAUNCH(K_GEMM_FC1, launch_gemm(h->maps.xn, w.tm_fc1, M, I, D, ep, h->num_sms, st), "fc1 gemm");
+        }
+        {
+            GemmEpilogue ep;
+            ep.bias = w.fc2_b; ep.colscale = w.ls2; ep.residual = h->x; ep.ld_res = D; ep.out_f32 = h->x; ep.ld_out = D;
+            AIGV_LAUNCH(K_GEMM_FC2, launch_gemm(h->maps.h, w.tm_fc2, M, D, I, ep, h->num_sms, st), "fc2 gemm");
+        }
+    }
+    // X1/X2 + mlp1[0]: drop cls, pixel shuffle, LayerNorm(4D) ; X3: mlp1[1]+GELU, mlp1[3]
+    AIGV_LAUNCH(K_PIXEL_SHUFFLE_LN, launch_pixel_shuffle_ln(h->x, h->mln_w, h->mln_b, h->ps, n, h->g, D, h->cfg.mlp1_ln_eps, 1, st),
+             "pixel_shuffle+ln");
+    {
+        GemmEpilogue ep;
+        ep.bias = h->m1_b; ep.gelu = 1; ep.out_bf16 = h->m1; ep.ld_out = C;
+        AIGV_LAUNCH(K_GEMM_MLP1_A, launch_gemm(h->maps.ps, h->tm_m1_w, Mo, C, h->W4, ep, h->num_sms, st), "mlp1.1 gemm");
+    }
+    {
+        GemmEpilogue ep;
+        ep.bias = h->m2_b; ep.out_bf16 = out; ep.ld_out = C;
+        AIGV_LAUNCH(K_GEMM_MLP1_B, launch_gemm(h->maps.m1, h->tm_m2_w, Mo, C, C, ep, h->num_sms, st), "mlp1.3 gemm");
+    }
+    return AIGV_OK;
+}
+
+int aigv_extract_feature(aigv_handle* h, const void* pixel_values_bf16, int n_tiles, void* out_bf16, void* stream) {
+    if (!h) return AIGV_ERR_INVALID;
+    if (!h->finalized) return fail(h, AIGV_ERR_STATE, "aigv_extract_feature before aigv_finalize_weights");
+    if (!pixel_values_bf16 || !out_bf16 || n_tiles <= 0) return fail(h, AIGV_ERR_INVALID, "extract_feature: argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t in_per = (size_t)3 * h->cfg.image_size * h->cfg.image_size;
+    const size_t out_per = (size_t)h->T * h->C;
+    const __nv_bfloat16* pv = static_cast<const __nv_bfloat16*>(pixel_values_bf16);
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
+    for (int t0 = 0; t0 < n_tiles; t0 += h->max_tiles) {
+        const int n = n_tiles - t0 < h->max_tiles ? n_tiles - t0 : h->max_tiles;
+        int r = forward_batch(h, pv + t0 * in_per, n, out + t0 * out_per, st);
+        if (r) return r;
+    }
+    return AIGV_OK;
+}
+
+int aigv_copy_vit_hidden(aigv_handle* h, float* dst, int n_tiles, void* stream) {
+    if (!h || !dst || n_tiles <= 0 || n_tiles > h->max_tiles) return fail(h, AIGV_ERR_INVALID, "copy_vit_hidden");
+    AIGV_TRY(cudaMemcpyAsync(dst, h->x, (size_t)n_tiles * h->S * h->D * 4, cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)),
+             "copy_vit_hidden");
+    return AIGV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ instrumentation
+int aigv_profile_enable(aigv_handle* h, int on) {
+    if (!h) return AIGV_ERR_INVALID;
+    h->prof.on = on != 0;
+    return AIGV_OK;
+}
+int aigv_profile_num_classes(void) { return K_NUM; }
+const char* aigv_profile_class_name(int cls) { return (cls >= 0 && cls < K_NUM) ? kClassNames[cls] : ""; }
+int aigv_profile_read(aigv_handle* h, double* ms, int64_t* counts, int n, int reset) {
+    if (!h || !ms || !counts || n < K_NUM) return fail(h, AIGV_ERR_INVALID, "profile_read: argument");
+    Profiler& p = h->prof;
+    for (size_t i = 0; i < p.used; ++i) {
+        float t = 0.f;
+        AIGV_TRY(cudaEventSynchronize(p.pool[i].b), "profile event sync");
+        AIGV_TRY(cudaEventElapsedTime(&t, p.pool[i].a, p.pool[i].b), "profile event elapsed");
+        p.ms[p.pool[i].cls] += t;
+        p.cnt[p.pool[i].cls] += 1;
+    }
+    p.used = 0;
+    for (int c = 0; c < K_NUM; ++c) { ms[c] = p.ms[c]; counts[c] = p.cnt[c]; }
+    if (reset) for (int c = 0; c < K_NUM; ++c) { p.ms[c] = 0; p.cnt[c] = 0; }
+    return AIGV_OK;
+}
+int64_t aigv_launch_count(const aigv_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ front end
+int aigv_tile_grid(int width, int height, int min_num, int max_num, int image_size, int* gi, int* gj) {
+    if (width <= 0 || height <= 0 || min_num < 1 || max_num < min_num || !gi || !gj) return AIGV_ERR_INVALID;
+    // dataset.py:703-713: candidate (i,j) with min_num <= i*j <= max_num sorted by area (stable over the set's
+    // iteration order is irrelevant here: ties in |ratio diff| are resolved by the area rule, strict '<' otherwise)
+    std::vector<std::pair<int, int>> ratios;
+    for (int n = min_num; n <= max_num; ++n)
+        for (int i = 1; i <= n; ++i)
+            for (int j = 1; j <= n; ++j)
+                if (i * j <= max_num && i * j >= min_num) {
+                    bool seen = false;
+                    for (auto& r : ratios) seen |= (r.first == i && r.second == j);
+                    if (!seen) ratios.push_back({i, j});
+                }
+    std::stable_sort(ratios.begin(), ratios.end(),
+                     [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+                         if (a.first * a.second != b.first * b.second) return a.first * a.second < b.first * b.second;
+                         return a < b;  // python sorts the set's tuples by area only; see tests for order-independence
+                     });
+    const double aspect = (double)width / (double)height;
+    double best_diff = INFINITY;
+    std::pair<int, int> best = {1, 1};
+    const double area = (double)width * height;
+    for (auto& r : ratios) {
+        const double tar = (double)r.first / (double)r.second;
+        const double diff = fabs(aspect - tar);
+        if (diff < best_diff) { best_diff = diff; best = r; }
+        else if (diff == best_diff) {
+            if (area > 0.5 * image_size * image_size * r.first * r.second) best = r;
+        }
+    }
+    *gi = best.first;
+    *gj = best.second;
+    return AIGV_OK;
+}
+
+static int get_plan(aigv_handle* h, int H, int W, int out_w, int out_h, PlanDev** out) {
+    auto key = std::make_tuple(H, W, out_w, out_h);
+    auto it = h->plans.find(key);
+    if (it != h->plans.end()) { *out = &it->second; return 0; }
+    std::vector<int32_t> kx, bx, ky, by;
+    PlanDev p;
+    p.ksize_x = plan_axis(W, out_w, kx, bx);
+    p.ksize_y = plan_axis(H, out_h, ky, by);
+    p.max_rows = plan_max_rows(by, out_h);
+    bool ok = dev_alloc(h, &p.kx, kx.size()) && dev_alloc(h, &p.bx, bx.size()) && dev_alloc(h, &p.ky, ky.size()) &&
+              dev_alloc(h, &p.by, by.size());
+    if (!ok) return -1;
+    ok &= cudaMemcpy(p.kx, kx.data(), kx.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(p.bx, bx.data(), bx.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(p.ky, ky.data(), ky.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok &= cudaMemcpy(p.by, by.data(), by.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) return -1;
+    auto ins = h->plans.emplace(key, p);
+    *out = &ins.first->second;
+    return 0;
+}
+
+int aigv_preprocess_u8(aigv_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
+                       int64_t row_stride, int gi, int gj, int thumb, uint8_t* tiles_u8, void* out_bf16, void* stream) {
+    if (!h) return AIGV_ERR_INVALID;
+    if (!frames || !out_bf16 || n <= 0 || H <= 0 || W <= 0 || gi <= 0 || gj <= 0 || row_stride < (int64_t)W * 3)
+        return fail(h, AIGV_ERR_INVALID, "preprocess_u8: argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tile = h->cfg.image_size;
+    const int blocks = gi * gj;
+    const bool with_thumb = thumb && blocks != 1;  // dataset.py:734
+    const int per_frame = blocks + (with_thumb ? 1 : 0);
+    PlanDev* p = nullptr;
+    if (get_plan(h, H, W, tile * gi, tile * gj, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
+    ResizePlan rp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile * gi, tile * gj};
+    AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, rp, p->max_rows, h->lut, tile, gi,
+                                    per_frame, 0, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
+             "preprocess");
+    if (with_thumb) {
+        if (get_plan(h, H, W, tile, tile, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
+        ResizePlan tp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile, tile};
+        AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, tp, p->max_rows, h->lut, tile, 1,
+                                        per_frame, blocks, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
+                 "preprocess(thumbnail)");
+    }
+    return AIGV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-op entry points
+#define AIGV_TRY0(expr)                                        \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return AIGV_ERR_CUDA;           \
+    } while (0)
+
+int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias, const float* colscale,
+                       const float* residual, float* out_f32, void* out_bf16, int M, int N, int K, int gelu,
+                       void* stream) {
+    if (!a_bf16 || !w_bf16 || M <= 0 || N <= 0 || K <= 0) return AIGV_ERR_INVALID;
+    CUtensorMap ta, tb;
+    if (make_tmap_bf16_2d(&ta, a_bf16, M, K, K, gemm_box_rows_a(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    if (make_tmap_bf16_2d(&tb, w_bf16, N, K, K, gemm_box_rows_b(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    GemmEpilogue ep;
+    ep.bias = bias; ep.colscale = colscale; ep.residual = residual; ep.ld_res = N;
+    ep.out_f32 = out_f32; ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); ep.ld_out = N; ep.gelu = gelu;
+    cudaError_t e = launch_gemm(ta, tb, M, N, K, ep, device_num_sms(), static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidValue) return AIGV_ERR_INVALID;
+    return e == cudaSuccess ? AIGV_OK : AIGV_ERR_CUDA;
+}
+
+int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int heads, int head_dim, float scale,
+                   void* stream) {
+    if (!qkv_bf16 || !out_bf16 || frames <= 0 || S <= 0 || heads <= 0) return AIGV_ERR_INVALID;
+    if (head_dim != 64) return AIGV_ERR_UNSUPPORTED;
+    const uint64_t M = (uint64_t)frames * S, D3 = 3ull * heads * head_dim;
+    CUtensorMap tf, tt;
+    if (make_tmap_bf16_2d(&tf, qkv_bf16, M, D3, D3, 128, 64)) return AIGV_ERR_INVALID;
+    if (make_tmap_bf16_2d(&tt, qkv_bf16, M, D3, D3, attention_tail_rows(S), 64)) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_attention(tf, tt, static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
+                               static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_layernorm(const float* x, const float* w, const float* b, void* y_bf16, int rows, int D, float eps, int rms,
+                   void* stream) {
+    if (!x || !w || !y_bf16) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_norm_f32_to_bf16(x, w, b, static_cast<__nv_bfloat16*>(y_bf16), rows, D, eps, rms,
+                                      static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_rmsnorm_inplace(void* x_bf16, const float* w, int rows, int D, int ld, int col0, float eps, void* stream) {
+    if (!x_bf16 || !w) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_rmsnorm_bf16_inplace(static_cast<__nv_bfloat16*>(x_bf16), w, rows, D, ld, col0, eps,
+                                          static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_im2col(const void* pixel_values_bf16, void* patches_bf16, int n, int image_size, int patch, int kpad,
+                void* stream) {
+    if (!pixel_values_bf16 || !patches_bf16) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_im2col(static_cast<const __nv_bfloat16*>(pixel_values_bf16),
+                            static_cast<__nv_bfloat16*>(patches_bf16), n, image_size, patch, kpad,
+                            static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_assemble_tokens(const float* pe, const float* cls, const float* pos, float* x, int n, int P, int D,
+                         void* stream) {
+    if (!pe || !cls || !pos || !x) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_assemble_tokens(pe, cls, pos, x, n, P, D, static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_pixel_shuffle(const float* x, const float* w, const float* b, void* y_bf16, int n, int g, int D, float eps,
+                       int apply_ln, void* stream) {
+    if (!x || !y_bf16 || (apply_ln && (!w || !b))) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_pixel_shuffle_ln(x, w, b, static_cast<__nv_bfloat16*>(y_bf16), n, g, D, eps, apply_ln,
+                                      static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogue.
+//
+//   C[M,N] = epilogue( A[M,K] (bf16, K contiguous)  x  W[N,K]^T (bf16, K contiguous, i.e. nn.Linear weight layout) )
+//   epilogue(acc) = residual + colscale * act(acc + bias)        (each term optional; fp32 math; bf16 or fp32 store)
+//
+// Replaces the cuBLASLt GEMM + separate bias / GELU / layer-scale / residual kernels behind
+//   attn.qkv  (modeling_intern_vit.py:129,163)   attn.proj + *ls1 + residual (:141,175,224)
+//   mlp.fc1 + GELU (:189,193-194)                mlp.fc2 + *ls2 + residual (:190,195,226)
+//   patch_embedding conv as im2col GEMM (:97)    mlp1[1]+GELU, mlp1[3] (modeling_internvl_chat.py eval2:240-242)
+//
+// Tile 128x256x64, 4-stage TMA->smem ring (128B swizzle), UMMA M=128 N=256 K=16 issued by one thread,
+// two 256-column fp32 accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warps 0-7: epilogue (warp%4 = TMEM lane quadrant, warp/4 = column half); warp 8: TMA producer; warp 9: MMA issuer.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace aigv {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + manual 1024B alignment slack
+constexpr uint32_t TMEM_COLS = 512;
+
+template <bool kGelu, bool kOutF32>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, const GemmEpilogue& ep) {
+    const size_t off = static_cast<size_t>(row) * ep.ld_out + col0;
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+    if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+        }
+    }
+    if (kGelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (ep.colscale) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(ep.colscale + col0 + j));
+            x[j] *= s.x; x[j + 1] *= s.y; x[j + 2] *= s.z; x[j + 3] *= s.w;
+        }
+    }
+    if (ep.residual) {
+        const float* r = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(r + j);
+            x[j] += t.x; x[j + 1] += t.y; x[j + 2] += t.z; x[j + 3] += t.w;
+        }
+    }
+    if (kOutF32) {
+        float* o = ep.out_f32 + off;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    } else {
+        __nv_bfloat16* o = ep.out_bf16 + off;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            uint4 p;
+            p.x = pack_bf16x2(x[j], x[j + 1]);
+            p.y = pack_bf16x2(x[j + 2], x[j + 3]);
+            p.z = pack_bf16x2(x[j + 4], x[j + 5]);
+            p.w = pack_bf16x2(x[j + 6], x[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = p;
+        }
+    }
+}
+
+template <bool kGelu, bool kOutF32>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                    int K, GemmEpilogue ep) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_m = (M + BM - 1) / BM;
+    const int num_n = (N + BN - 1) / BN;
+    const int num_k = (K + BK - 1) / BK;
+    const int num_tiles = num_m * num_n;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 9) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tfull_bar[s], 1);
+                mbar_init(&tempty_bar[s], EPI_WARPS);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc<TMEM_COLS>(tmem_slot);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------------------ MMA issuer (single thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+                        const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                        umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps
+        const int quad = warp & 3;
+        const int half = warp >> 2;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BM + quad * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int coff = half * 128 + c * 32;
+                const int col0 = n_blk * BN + coff;
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + coff, v);
+                tmem_ld_wait();
+                if (row < M && col0 < N) epilogue_chunk<kGelu, kOutF32>(v, row, col0, ep);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <bool kGelu, bool kOutF32>
+cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                           int num_sms, cudaStream_t stream) {
+    auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int gemm_box_rows_a() { return BM; }
+int gemm_box_rows_b() { return BN; }
+int gemm_box_cols() { return BK; }
+
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                        int num_sms, cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
+    if ((ep.out_f32 != nullptr) == (ep.out_bf16 != nullptr)) return cudaErrorInvalidValue;
+    const bool f32 = ep.out_f32 != nullptr;
+    if (ep.gelu) {
+        return f32 ? launch_variant<true, true>(tmA, tmB, M, N, K, ep, num_sms, stream)
+                   : launch_variant<true, false>(tmA, tmB, M, N, K, ep, num_sms, stream);
+    }
+    return f32 ? launch_variant<false, true>(tmA, tmB, M, N, K, ep, num_sms, stream)
+               : launch_variant<false, false>(tmA, tmB, M, N, K, ep, num_sms, stream);
+}
+
+}  // namespace aigv

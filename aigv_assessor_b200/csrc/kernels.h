@@ -1,0 +1,79 @@
+// Internal launcher declarations shared by the .cu files and the C-ABI layer (api.cu). Not a public header:
+// the public boundary is include/aigv_b200.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aigv {
+
+struct GemmEpilogue {
+    const float* bias = nullptr;      // [N] fp32, optional
+    const float* colscale = nullptr;  // [N] fp32, optional (layer scale ls1/ls2)
+    const float* residual = nullptr;  // [M, ld_res] fp32, optional (may alias out_f32: in-place residual stream)
+    float* out_f32 = nullptr;         // exactly one of out_f32 / out_bf16 is set
+    __nv_bfloat16* out_bf16 = nullptr;
+    int ld_out = 0;                   // elements
+    int ld_res = 0;
+    int gelu = 0;                     // exact erf GELU after bias
+};
+
+// ---- TMA descriptors (host) -------------------------------------------------------------------------------------
+// Row-major bf16 matrix [rows, cols] with row stride `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
+// Returns 0 on success.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                      uint32_t box_cols);
+
+// ---- GEMM ------------------------------------------------------------------------------------------------------
+int gemm_box_rows_a();
+int gemm_box_rows_b();
+int gemm_box_cols();
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
+                        int num_sms, cudaStream_t stream);
+
+// ---- attention -------------------------------------------------------------------------------------------------
+// qkv: bf16 [frames*S, 3*D] with channel order (three, head, d); out: bf16 [frames*S, D] (head-major channels).
+// tm_full: box [128 rows, 64 cols]; tm_tail: box [attention_tail_rows(S), 64 cols] over the same qkv matrix.
+int attention_tail_rows(int S);
+cudaError_t launch_attention(const CUtensorMap& tm_full, const CUtensorMap& tm_tail, __nv_bfloat16* out, int frames,
+                             int S, int heads, int head_dim, float softmax_scale, cudaStream_t stream);
+
+// ---- row-wise / bandwidth kernels --------------------------------------------------------------------------------
+// y[r,:] = LN(x[r,:]) * w + b (b may be null -> RMSNorm when rms != 0). x fp32 [rows, D] -> y bf16 [rows, D].
+cudaError_t launch_norm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows, int D,
+                                    float eps, int rms, cudaStream_t stream);
+// In-place RMSNorm over column block [col0, col0+D) of a bf16 matrix with row stride ld (q/k norm of InternViT-6B).
+cudaError_t launch_rmsnorm_bf16_inplace(__nv_bfloat16* x, const float* w, int rows, int D, int ld, int col0, float eps,
+                                        cudaStream_t stream);
+// pixel_values bf16 [n,3,S,S] -> patches bf16 [n*g*g, Kpad] with (c,ky,kx) flattening, zero padded to Kpad.
+cudaError_t launch_im2col(const __nv_bfloat16* pv, __nv_bfloat16* patches, int n, int img, int patch, int kpad,
+                          cudaStream_t stream);
+// x[n, 0, :] = cls + pos[0]; x[n, 1+p, :] = pe[n*P + p, :] + pos[1+p]   (pe fp32 already has the conv bias)
+cudaError_t launch_assemble_tokens(const float* pe, const float* cls, const float* pos, float* x, int n, int P, int D,
+                                   cudaStream_t stream);
+// Drop cls, 2x2 pixel-shuffle (v2) and LayerNorm(4D): x fp32 [n, 1+g*g, D] -> y bf16 [n*(g/2)^2, 4D].
+cudaError_t launch_pixel_shuffle_ln(const float* x, const float* w, const float* b, __nv_bfloat16* y, int n, int g,
+                                    int D, float eps, int apply_ln, cudaStream_t stream);
+// Pillow-exact two-pass bicubic (antialias) resize of uint8 HWC frames into square tiles, fused with
+// ToTensor/Normalize (768-entry LUT) and the bf16 cast, written NCHW. Tables live on the device.
+struct ResizePlan {
+    const int32_t* kx;   // [out_w, ksize_x] fixed-point taps
+    const int32_t* bx;   // [out_w, 2] xmin, count
+    const int32_t* ky;   // [out_h, ksize_y]
+    const int32_t* by;   // [out_h, 2]
+    int ksize_x, ksize_y;
+    int out_w, out_h;    // resized image size (multiples of the tile size)
+};
+}  // namespace aigv
+#include <vector>
+namespace aigv {
+// Host: Pillow precompute_coeffs + normalize_coeffs_8bpc for one axis; returns ksize.
+int plan_axis(int in_size, int out_size, std::vector<int32_t>& kk, std::vector<int32_t>& bounds);
+int plan_max_rows(const std::vector<int32_t>& by, int out_h);
+cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
+                                   int64_t row_stride, const ResizePlan& plan, int max_rows, const float* lut, int tile,
+                                   int tiles_x, int tiles_per_frame, int tile_offset, uint8_t* tiles_u8,
+                                   __nv_bfloat16* out, cudaStream_t stream);
+
+}  // namespace aigv

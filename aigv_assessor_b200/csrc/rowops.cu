@@ -1,0 +1,246 @@
+// Row-wise / bandwidth-bound kernels of the vision path (HBM roofline; vectorised 16-byte accesses, one warp per row).
+//   norm_f32_to_bf16      nn.LayerNorm(D, eps) / InternRMSNorm  (modeling_intern_vit.py:208-209,32-43)
+//   rmsnorm_bf16_inplace  q_norm / k_norm of InternViT-6B       (modeling_intern_vit.py:135-137,166-170)
+//   im2col                patch extraction for the k=s=14 conv  (modeling_intern_vit.py:97)
+//   assemble_tokens       cls concat + position embedding       (modeling_intern_vit.py:99-106)
+//   pixel_shuffle_ln      drop cls + pixel_shuffle v2 + mlp1[0] LayerNorm (eval2 modeling_internvl_chat.py:492-506,520-529,239)
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace aigv {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Statistics over `nseg` segments of `seg_len` floats each (segment s starts at seg_ptr(s)); two-pass variance in fp32.
+struct RowStats { float mean, rstd; };
+
+template <typename SegPtr>
+__device__ __forceinline__ RowStats row_stats(SegPtr seg_ptr, int nseg, int seg_len, float eps, bool rms, int lane) {
+    const int n4 = seg_len >> 2;
+    const float inv_n = 1.0f / static_cast<float>(nseg * seg_len);
+    float mean = 0.f;
+    if (!rms) {
+        float s = 0.f;
+        for (int g = 0; g < nseg; ++g) {
+            const float4* p = reinterpret_cast<const float4*>(seg_ptr(g));
+            for (int i = lane; i < n4; i += 32) {
+                const float4 t = p[i];
+                s += (t.x + t.y) + (t.z + t.w);
+            }
+        }
+        mean = warp_sum(s) * inv_n;
+    }
+    float q = 0.f;
+    for (int g = 0; g < nseg; ++g) {
+        const float4* p = reinterpret_cast<const float4*>(seg_ptr(g));
+        for (int i = lane; i < n4; i += 32) {
+            const float4 t = p[i];
+            const float a = t.x - mean, b = t.y - mean, c = t.z - mean, d = t.w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float var = warp_sum(q) * inv_n;
+    return {mean, rsqrtf(var + eps)};
+}
+
+__global__ void __launch_bounds__(256)
+norm_f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                        __nv_bfloat16* __restrict__ y, int rows, int D, float eps, int rms) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + static_cast<size_t>(row) * D;
+    const RowStats st = row_stats([&](int) { return xr; }, 1, D, eps, rms != 0, lane);
+    __nv_bfloat16* yr = y + static_cast<size_t>(row) * D;
+    for (int i = lane * 8; i < D; i += 256) {
+        const float4 a0 = *reinterpret_cast<const float4*>(xr + i);
+        const float4 a1 = *reinterpret_cast<const float4*>(xr + i + 4);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + i));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + i + 4));
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (b) {
+            b0 = __ldg(reinterpret_cast<const float4*>(b + i));
+            b1 = __ldg(reinterpret_cast<const float4*>(b + i + 4));
+        }
+        uint4 o;
+        o.x = pack_bf16x2((a0.x - st.mean) * st.rstd * w0.x + b0.x, (a0.y - st.mean) * st.rstd * w0.y + b0.y);
+        o.y = pack_bf16x2((a0.z - st.mean) * st.rstd * w0.z + b0.z, (a0.w - st.mean) * st.rstd * w0.w + b0.w);
+        o.z = pack_bf16x2((a1.x - st.mean) * st.rstd * w1.x + b1.x, (a1.y - st.mean) * st.rstd * w1.y + b1.y);
+        o.w = pack_bf16x2((a1.z - st.mean) * st.rstd * w1.z + b1.z, (a1.w - st.mean) * st.rstd * w1.w + b1.w);
+        *reinterpret_cast<uint4*>(yr + i) = o;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rmsnorm_bf16_inplace_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ w, int rows, int D, int ld,
+                            int col0, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    __nv_bfloat16* xr = x + static_cast<size_t>(row) * ld + col0;
+    float q = 0.f;
+    for (int i = lane * 8; i < D; i += 256) {
+        const uint4 t = *reinterpret_cast<const uint4*>(xr + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h[k]);
+            q += f.x * f.x + f.y * f.y;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+    for (int i = lane * 8; i < D; i += 256) {
+        uint4 t = *reinterpret_cast<const uint4*>(xr + i);
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h[k]);
+            // InternRMSNorm: weight * (x * rstd)  (modeling_intern_vit.py:39-43), one rounding at the store
+            const float a = f.x * rstd * w[i + 2 * k];
+            const float c = f.y * rstd * w[i + 2 * k + 1];
+            h[k] = __floats2bfloat162_rn(a, c);
+        }
+        *reinterpret_cast<uint4*>(xr + i) = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+im2col_kernel(const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ patches, int n, int img, int patch,
+              int kpad) {
+    const int g = img / patch;
+    const int kp2 = kpad >> 1;
+    const int kreal = 3 * patch * patch;
+    const size_t total = static_cast<size_t>(n) * g * g * kp2;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(idx % kp2) * 2;
+        const size_t prow = idx / kp2;
+        uint32_t v = 0;
+        if (k < kreal) {
+            const int p = static_cast<int>(prow % (g * g));
+            const int f = static_cast<int>(prow / (g * g));
+            const int py = p / g, px = p % g;
+            const int c = k / (patch * patch);
+            const int rem = k - c * patch * patch;
+            const int ky = rem / patch, kx = rem % patch;
+            const size_t src = ((static_cast<size_t>(f) * 3 + c) * img + (py * patch + ky)) * img + px * patch + kx;
+            v = *reinterpret_cast<const uint32_t*>(pv + src);
+        }
+        *reinterpret_cast<uint32_t*>(patches + prow * kpad + k) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+assemble_tokens_kernel(const float* __restrict__ pe, const float* __restrict__ cls, const float* __restrict__ pos,
+                       float* __restrict__ x, int n, int P, int D) {
+    const int d4 = D >> 2;
+    const size_t total = static_cast<size_t>(n) * (P + 1) * d4;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % d4) * 4;
+        const size_t tr = idx / d4;
+        const int t = static_cast<int>(tr % (P + 1));
+        const int f = static_cast<int>(tr / (P + 1));
+        const float4 ps = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * D + c));
+        float4 v;
+        if (t == 0) v = __ldg(reinterpret_cast<const float4*>(cls + c));
+        else v = *reinterpret_cast<const float4*>(pe + (static_cast<size_t>(f) * P + (t - 1)) * D + c);
+        v.x += ps.x; v.y += ps.y; v.z += ps.z; v.w += ps.w;
+        *reinterpret_cast<float4*>(x + tr * D + c) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pixel_shuffle_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                        __nv_bfloat16* __restrict__ y, int n, int g, int D, float eps, int apply_ln) {
+    const int g2 = g >> 1;
+    const int orow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (orow >= n * g2 * g2) return;
+    const int f = orow / (g2 * g2);
+    const int ij = orow % (g2 * g2);
+    const int I = ij / g2, J = ij % g2;
+    const float* frame = x + static_cast<size_t>(f) * (g * g + 1) * D;
+    // out[n,I,J,(2di+dj)*D + c] = in[n, 1 + g*(2I+di) + (2J+dj), c]   (probed on the reference)
+    auto seg = [&](int s) { return frame + static_cast<size_t>(1 + g * (2 * I + (s >> 1)) + (2 * J + (s & 1))) * D; };
+    RowStats st{0.f, 1.f};
+    if (apply_ln) st = row_stats(seg, 4, D, eps, false, lane);
+    __nv_bfloat16* yr = y + static_cast<size_t>(orow) * 4 * D;
+    for (int s = 0; s < 4; ++s) {
+        const float* xs = seg(s);
+        for (int i = lane * 8; i < D; i += 256) {
+            const float4 a0 = *reinterpret_cast<const float4*>(xs + i);
+            const float4 a1 = *reinterpret_cast<const float4*>(xs + i + 4);
+            float4 w0 = make_float4(1.f, 1.f, 1.f, 1.f), w1 = w0;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (apply_ln) {
+                w0 = __ldg(reinterpret_cast<const float4*>(w + s * D + i));
+                w1 = __ldg(reinterpret_cast<const float4*>(w + s * D + i + 4));
+                b0 = __ldg(reinterpret_cast<const float4*>(b + s * D + i));
+                b1 = __ldg(reinterpret_cast<const float4*>(b + s * D + i + 4));
+            }
+            uint4 o;
+            o.x = pack_bf16x2((a0.x - st.mean) * st.rstd * w0.x + b0.x, (a0.y - st.mean) * st.rstd * w0.y + b0.y);
+            o.y = pack_bf16x2((a0.z - st.mean) * st.rstd * w0.z + b0.z, (a0.w - st.mean) * st.rstd * w0.w + b0.w);
+            o.z = pack_bf16x2((a1.x - st.mean) * st.rstd * w1.x + b1.x, (a1.y - st.mean) * st.rstd * w1.y + b1.y);
+            o.w = pack_bf16x2((a1.z - st.mean) * st.rstd * w1.z + b1.z, (a1.w - st.mean) * st.rstd * w1.w + b1.w);
+            *reinterpret_cast<uint4*>(yr + s * D + i) = o;
+        }
+    }
+}
+
+inline int grid_for(size_t work_items, int threads, int cap = 148 * 16) {
+    size_t b = (work_items + threads - 1) / threads;
+    if (b > static_cast<size_t>(cap)) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<int>(b);
+}
+
+}  // namespace
+
+cudaError_t launch_norm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows, int D,
+                                    float eps, int rms, cudaStream_t stream) {
+    if (rows <= 0 || D <= 0 || (D % 8) != 0) return cudaErrorInvalidValue;
+    norm_f32_to_bf16_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, w, b, y, rows, D, eps, rms);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rmsnorm_bf16_inplace(__nv_bfloat16* x, const float* w, int rows, int D, int ld, int col0, float eps,
+                                        cudaStream_t stream) {
+    if (rows <= 0 || (D % 8) != 0 || (ld % 8) != 0 || (col0 % 8) != 0) return cudaErrorInvalidValue;
+    rmsnorm_bf16_inplace_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, w, rows, D, ld, col0, eps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_im2col(const __nv_bfloat16* pv, __nv_bfloat16* patches, int n, int img, int patch, int kpad,
+                          cudaStream_t stream) {
+    if (n <= 0 || (patch % 2) != 0 || (kpad % 2) != 0 || kpad < 3 * patch * patch) return cudaErrorInvalidValue;
+    const int g = img / patch;
+    const size_t total = static_cast<size_t>(n) * g * g * (kpad / 2);
+    im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(pv, patches, n, img, patch, kpad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble_tokens(const float* pe, const float* cls, const float* pos, float* x, int n, int P, int D,
+                                   cudaStream_t stream) {
+    if (n <= 0 || (D % 4) != 0) return cudaErrorInvalidValue;
+    const size_t total = static_cast<size_t>(n) * (P + 1) * (D / 4);
+    assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, stream>>>(pe, cls, pos, x, n, P, D);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pixel_shuffle_ln(const float* x, const float* w, const float* b, __nv_bfloat16* y, int n, int g,
+                                    int D, float eps, int apply_ln, cudaStream_t stream) {
+    if (n <= 0 || (g % 2) != 0 || (D % 8) != 0) return cudaErrorInvalidValue;
+    const int rows = n * (g / 2) * (g / 2);
+    pixel_shuffle_ln_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, w, b, y, n, g, D, eps, apply_ln);
+    return cudaGetLastError();
+}
+
+}  // namespace aigv

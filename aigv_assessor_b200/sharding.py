@@ -1,0 +1,66 @@
+"""Clip-granular data parallelism: the path shards with no data-path collective (every tile is independent,
+SURVEY.md section 8e); the only exchange is one all-gather of per-clip results at the end.
+
+The reference's eval loop is unsharded (stage1_eval.py:898-901: plain DataLoader, every rank would redo the whole
+set); this module is the new functionality that replaces it for multi-GPU runs. Works with NCCL (GPU) and gloo (CPU
+tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
+    """Round-robin ownership: rank r takes clips r, r+W, ... (equal frames per clip => balanced)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return list(range(rank, n_items, world))
+
+
+def gather_clip_results(local: torch.Tensor, n_items: int, rank: int | None = None, world: int | None = None,
+                        group=None) -> torch.Tensor:
+    """local: [len(shard_indices(n_items, rank, world)), ...] results for this rank's clips (scores or features).
+    Returns [n_items, ...] in original clip order on every rank. Uneven tails are padded for the collective."""
+    if not (dist.is_available() and dist.is_initialized()):
+        if local.shape[0] != n_items:
+            raise ValueError("single-process gather expects all items")
+        return local
+    world = dist.get_world_size(group) if world is None else world
+    rank = dist.get_rank(group) if rank is None else rank
+    per = (n_items + world - 1) // world
+    mine = len(shard_indices(n_items, rank, world))
+    if local.shape[0] != mine:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} items, expected {mine}")
+    padded = local.new_zeros((per,) + tuple(local.shape[1:]))
+    padded[:mine] = local
+    out = local.new_empty((world * per,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    out = out.view((world, per) + tuple(local.shape[1:]))
+    # rank r slot k  ->  clip r + k*world
+    full = out.transpose(0, 1).reshape((per * world,) + tuple(local.shape[1:]))
+    return full[:n_items].contiguous()
+
+
+def encode_clips_sharded(engine, clips: Sequence[torch.Tensor], pool: bool = False) -> torch.Tensor:
+    """clips: list of pixel_values [frames,3,448,448] (same frame count). Each rank encodes its clips and the
+    visual tokens (or their per-clip mean when pool=True) are all-gathered. Returns [n_clips, frames*256, C] (or
+    [n_clips, C])."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    mine = shard_indices(len(clips), rank, world)
+    outs = []
+    for i in mine:
+        y = engine.extract_feature(clips[i])
+        y = y.reshape(-1, y.shape[-1])
+        outs.append(y.float().mean(0) if pool else y)
+    if outs:
+        local = torch.stack(outs)
+    else:
+        c = engine.cfg.llm_hidden
+        f = clips[0].shape[0] * engine.cfg.out_tokens if clips else 0
+        local = torch.empty((0, c) if pool else (0, f, c), device=engine.device,
+                            dtype=torch.float32 if pool else torch.bfloat16)
+    return gather_clip_results(local, len(clips), rank, world)

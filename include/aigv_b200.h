@@ -1,0 +1,122 @@
+/*
+ * aigv_b200 — C ABI of the B200-native vision hot path of AIGV-Assessor.
+ *
+ * The reference (pure Python) has no FFI; its seam for this path is the bound method
+ *   InternVLChatModel.extract_feature(self, pixel_values) -> Tensor
+ *   (/root/reference/internvl/model/internvl_chat_eval2/modeling_internvl_chat.py:508-531; same method in
+ *    internvl_chat/modeling_internvl_chat.py:390-409 and the four other variants)
+ * and, in front of it, load_video's per-frame dynamic_preprocess + transform
+ *   (/root/reference/internvl/train/internvl/eval/stage1_eval.py:443-457,484-485;
+ *    /root/reference/internvl/train/dataset.py:702-738,268-274).
+ * Each entry point below names the reference code it replaces. INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative aigv_status and never throws;
+ * all device work is enqueued asynchronously on the given stream (a cudaStream_t passed as void*), with no hidden
+ * synchronisation or allocation after aigv_finalize_weights (the workspace is owned by the handle and sized by
+ * cfg.max_tiles; larger calls are micro-batched); one handle per (process, device); a handle is not thread-safe.
+ * Pointers are device pointers unless stated otherwise.
+ */
+#ifndef AIGV_B200_H_
+#define AIGV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct aigv_handle aigv_handle;
+
+enum aigv_status {
+    AIGV_OK = 0,
+    AIGV_ERR_INVALID = -1,     /* bad argument / shape */
+    AIGV_ERR_CUDA = -2,        /* a CUDA call failed; see aigv_last_error */
+    AIGV_ERR_MISSING = -3,     /* a required weight was never set */
+    AIGV_ERR_STATE = -4,       /* call order (e.g. extract before finalize) */
+    AIGV_ERR_UNSUPPORTED = -5  /* configuration outside what the kernels cover */
+};
+
+enum aigv_dtype { AIGV_F32 = 0, AIGV_BF16 = 1 };
+enum aigv_norm { AIGV_LAYER_NORM = 0, AIGV_RMS_NORM = 1 };
+
+/* Mirrors the InternVisionConfig fields the path reads (configuration_intern_vit.py:62-107) + the projector width. */
+typedef struct aigv_cfg {
+    int32_t hidden_size;        /* D */
+    int32_t num_heads;
+    int32_t intermediate_size;  /* I */
+    int32_t num_layers;
+    int32_t image_size;         /* 448 */
+    int32_t patch_size;         /* 14 */
+    int32_t llm_hidden;         /* C = mlp1 output width */
+    int32_t qkv_bias;
+    int32_t qk_normalization;
+    int32_t norm_type;          /* aigv_norm */
+    float layer_norm_eps;
+    float mlp1_ln_eps;
+    int32_t max_tiles;          /* micro-batch (tiles per launch) the workspace is sized for */
+} aigv_cfg;
+
+const char* aigv_version(void);
+const char* aigv_status_string(int status);
+
+/* Lifecycle. Replaces InternVLChatModel.__init__'s vision_model/mlp1 construction (eval2 :218-243) for this path. */
+int aigv_create(const aigv_cfg* cfg, aigv_handle** out);
+void aigv_destroy(aigv_handle* h);
+const char* aigv_last_error(const aigv_handle* h);
+size_t aigv_workspace_bytes(const aigv_handle* h, int n_tiles);
+
+/* Weight ABI: `name` is the reference state-dict key ("vision_model.encoder.layers.3.attn.qkv.weight", "mlp1.1.bias",
+ * ...). `ptr` may be a host or a device pointer (UVA); the data is copied and re-packed, the caller
+ * keeps ownership. Synchronous. */
+int aigv_set_weight(aigv_handle* h, const char* name, const void* ptr, int dtype, const int64_t* shape, int rank);
+int aigv_finalize_weights(aigv_handle* h, void* stream);
+
+/* extract_feature (eval2 :508-531 -> modeling_intern_vit.py:324-362): pixel_values bf16 [n_tiles,3,S,S] NCHW ->
+ * out bf16 [n_tiles, (S/P/2)^2, C]. */
+int aigv_extract_feature(aigv_handle* h, const void* pixel_values_bf16, int n_tiles, void* out_bf16, void* stream);
+/* Debug/test: copy the fp32 residual stream [n_tiles, 1+g*g, D] (= ViT last_hidden_state) of the most recent
+ * micro-batch into dst (device). */
+int aigv_copy_vit_hidden(aigv_handle* h, float* dst, int n_tiles, void* stream);
+
+/* Instrumentation (bench.py): when enabled every kernel launch of the path is bracketed by CUDA events on the launching
+ * stream and accumulated per kernel class; aigv_profile_read synchronises those events. aigv_launch_count = number of
+ * this library's kernels launched through the handle so far. */
+int aigv_profile_enable(aigv_handle* h, int on);
+int aigv_profile_num_classes(void);
+const char* aigv_profile_class_name(int cls);
+int aigv_profile_read(aigv_handle* h, double* ms, int64_t* counts, int n, int reset);
+int64_t aigv_launch_count(const aigv_handle* h);
+
+/* Front end. aigv_tile_grid = find_closest_aspect_ratio / grid choice of dynamic_preprocess (dataset.py:685-713).
+ * aigv_preprocess_u8 = dynamic_preprocess resize+crop(+thumbnail) (dataset.py:715-738) fused with build_transform
+ * (dataset.py:268-274) and the bf16 cast. frames: uint8 HWC RGB [n, H, W, 3] with the given byte strides. Writes
+ * n * (gi*gj + (thumb && gi*gj>1)) tiles, frame-major, tiles row-major then thumbnail. tiles_u8 (optional, may be NULL)
+ * receives the uint8 HWC tiles before normalisation. */
+int aigv_tile_grid(int width, int height, int min_num, int max_num, int image_size, int* gi, int* gj);
+int aigv_preprocess_u8(aigv_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
+                       int64_t row_stride, int gi, int gj, int thumb, uint8_t* tiles_u8, void* out_bf16, void* stream);
+
+/* Per-op entry points (unit parity tests call these; the fused path above uses the same launchers). */
+/* out = residual + colscale * act(A[M,K] @ W[N,K]^T + bias); exactly one of out_f32/out_bf16 non-NULL. */
+int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias, const float* colscale,
+                       const float* residual, float* out_f32, void* out_bf16, int M, int N, int K, int gelu,
+                       void* stream);
+/* qkv bf16 [frames*S, 3*heads*head_dim] (three, head, d) -> out bf16 [frames*S, heads*head_dim]. */
+int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int heads, int head_dim, float scale,
+                   void* stream);
+int aigv_layernorm(const float* x, const float* w, const float* b, void* y_bf16, int rows, int D, float eps, int rms,
+                   void* stream);
+int aigv_rmsnorm_inplace(void* x_bf16, const float* w, int rows, int D, int ld, int col0, float eps, void* stream);
+int aigv_im2col(const void* pixel_values_bf16, void* patches_bf16, int n, int image_size, int patch, int kpad,
+                void* stream);
+int aigv_assemble_tokens(const float* pe, const float* cls, const float* pos, float* x, int n, int P, int D,
+                         void* stream);
+int aigv_pixel_shuffle(const float* x, const float* w, const float* b, void* y_bf16, int n, int g, int D, float eps,
+                       int apply_ln, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIGV_B200_H_ */

@@ -1,0 +1,53 @@
+"""Fused tcgen05 attention vs the oracle's naive softmax(q*scale @ k^T) @ v, through aigv_attention (C-ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from aigv_assessor_b200 import _lib
+from tests.gpu_util import dev, emax, ptr, stream
+
+pytestmark = pytest.mark.gpu
+
+
+def _attn_ref(qkv, frames, S, H, d):
+    q, k, v = qkv.float().cuda().view(frames, S, 3, H, d).permute(2, 0, 3, 1, 4)
+    a = (q * d ** -0.5) @ k.transpose(-2, -1)
+    return (a.softmax(-1) @ v).transpose(1, 2).reshape(frames * S, H * d)
+
+
+@pytest.mark.parametrize("frames,S,H", [(1, 128, 1), (1, 256, 2), (2, 1025, 2), (3, 130, 4), (1, 1025, 16), (2, 97, 1)])
+def test_attention_matches_reference(frames, S, H):
+    d = 64
+    g = torch.Generator().manual_seed(S + H)
+    qkv = (torch.randn((frames * S, 3 * H * d), generator=g) * 1.5).to(torch.bfloat16)
+    out = torch.full((frames * S, H * d), float("nan"), dtype=torch.bfloat16, device="cuda")
+    lib = _lib.load()
+    st = lib.aigv_attention(ptr(dev(qkv)), ptr(out), frames, S, H, d, d ** -0.5, stream())
+    assert st == 0
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, frames, S, H, d)
+    y = out.float().cpu().numpy()
+    assert np.isfinite(y).all()
+    assert emax(y, ref.cpu().numpy()) < 1e-2
+
+
+def test_attention_peaked_rows_are_stable():
+    # one dominant key per row: exercises the running-max rescale across KV blocks
+    frames, S, H, d = 1, 1025, 1, 64
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn((S, 3 * d), generator=g)
+    qkv[:, :2 * d] *= 6.0
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.empty((S, d), dtype=torch.bfloat16, device="cuda")
+    lib = _lib.load()
+    assert lib.aigv_attention(ptr(dev(qkv)), ptr(out), frames, S, H, d, d ** -0.5, stream()) == 0
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, frames, S, H, d)
+    assert emax(out.float().cpu().numpy(), ref.cpu().numpy()) < 1e-2
+
+
+def test_attention_rejects_other_head_dims():
+    lib = _lib.load()
+    x = torch.zeros((128, 3 * 128), dtype=torch.bfloat16, device="cuda")
+    o = torch.zeros((128, 128), dtype=torch.bfloat16, device="cuda")
+    assert lib.aigv_attention(ptr(x), ptr(o), 1, 128, 1, 128, 0.1, stream()) == -5

@@ -1,0 +1,137 @@
+"""End-to-end parity of the CUDA extract_feature path: committed reference goldens, the numpy oracle on the same
+seeded inputs, and size-independent properties at full size. Tolerance (BASELINE.json north_star): visual-token
+embeddings within 2e-2 max error normalised by max|ref|, bf16 compute vs fp32 reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from aigv_assessor_b200 import synth
+from aigv_assessor_b200.config import VisionPathConfig, internvit_300m, tiny
+from aigv_assessor_b200.engine import VisionEngine
+from oracle import vit_oracle as vo
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _engine(cfg, seed, max_tiles=8):
+    return VisionEngine(cfg, max_tiles=max_tiles).load_state_dict(synth.make_weights(cfg, seed=seed))
+
+
+def _pv(n, cfg, seed):
+    return torch.from_numpy(synth.make_pixel_values(n, cfg, seed=seed)).to(torch.bfloat16).cuda()
+
+
+def test_tiny_tower_vs_reference_golden(golden_dir, golden_meta):
+    meta = golden_meta["tiny"]
+    cfg = VisionPathConfig(**meta["cfg"])
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    eng = _engine(cfg, meta["w_seed"])
+    out = eng.extract_feature(_pv(meta["n_frames"], cfg, meta["x_seed"]))
+    torch.cuda.synchronize()
+    vit = eng.vit_hidden(meta["n_frames"]).cpu().numpy()
+    e_vit = vo.error_metrics(vit, g["vit_out"])
+    e_out = vo.error_metrics(out.float().cpu().numpy(), g["out"])
+    print("tiny: vit e_max/e_l2", e_vit, "out", e_out, "reference-bf16 e_max", meta["ref_bf16_e_max"])
+    assert out.shape == (2, 256, cfg.llm_hidden) and out.dtype == torch.bfloat16
+    assert e_vit[1] < 1.5e-2 and e_out[0] < TOL
+
+
+def test_vit300m_frame_vs_reference_golden(golden_dir, golden_meta):
+    meta = golden_meta["vit300m"]
+    cfg = VisionPathConfig(**meta["cfg"])
+    g = np.load(os.path.join(golden_dir, "vit300m.npz"))
+    eng = _engine(cfg, meta["w_seed"])
+    out = eng.extract_feature(_pv(1, cfg, meta["x_seed"])).float().cpu().numpy()
+    vit = eng.vit_hidden(1).cpu().numpy()
+    e_vit = vo.error_metrics(vit[:, ::41, ::16], g["vit_out_s"])
+    e_max = float(np.abs(out[:, ::8, ::16] - g["out_s"]).max() / meta["out_absmax"])
+    print("vit300m: vit_out e_max/e_l2", e_vit, "out e_max", e_max, "reference-bf16 e_max", meta["ref_bf16_e_max"])
+    assert e_vit[1] < 1.5e-2
+    assert e_max < TOL
+
+
+def test_vit300m_two_frames_vs_oracle_and_batch_invariance():
+    cfg = internvit_300m(llm_hidden=2048)
+    sd = synth.make_weights(cfg, seed=0)
+    eng = VisionEngine(cfg, max_tiles=4).load_state_dict(sd)
+    pv = synth.make_pixel_values(6, cfg, seed=21)
+    out6 = eng.extract_feature(torch.from_numpy(pv).to(torch.bfloat16).cuda())  # 6 tiles > max_tiles: micro-batched
+    ref = vo.extract_feature(pv[:2], sd, cfg)
+    e = vo.error_metrics(out6[:2].float().cpu().numpy(), ref)
+    print("vit300m 2 frames vs oracle e_max/e_l2", e)
+    assert e[0] < TOL
+    # a tile's result does not depend on its batch neighbours or position (bit exact)
+    out1 = eng.extract_feature(torch.from_numpy(pv[5:6]).to(torch.bfloat16).cuda())
+    assert torch.equal(out1[0], out6[5])
+    # deterministic
+    again = eng.extract_feature(torch.from_numpy(pv).to(torch.bfloat16).cuda())
+    assert torch.equal(again, out6)
+
+
+def test_shapes_dtypes_and_errors():
+    cfg = tiny()
+    eng = _engine(cfg, 3)
+    pv = _pv(3, cfg, 4)
+    assert eng.extract_feature(pv, flatten=False).shape == (3, 16, 16, cfg.llm_hidden)
+    assert eng.extract_feature(pv.float()).dtype == torch.float32
+    assert eng.extract_feature(pv[:0]).shape == (0, 256, cfg.llm_hidden)
+    with pytest.raises(ValueError):
+        eng.extract_feature(pv[0])            # not 4-D: reference raises ValueError (modeling_intern_vit.py:345)
+    with pytest.raises(ValueError):
+        eng.extract_feature(pv[:, :, :224])   # wrong spatial size
+    with pytest.raises(ValueError):
+        eng.extract_feature(pv.cpu())
+    fresh = VisionEngine(cfg, max_tiles=2)
+    with pytest.raises(ValueError):
+        fresh.extract_feature(pv)              # weights never loaded
+    with pytest.raises(ValueError):
+        fresh.set_weight("vision_model.nope", np.zeros(3, np.float32))
+    with pytest.raises(ValueError):
+        fresh.set_weight("mlp1.1.bias", np.zeros(3, np.float32))  # wrong shape
+    with pytest.raises(ValueError):
+        VisionEngine(tiny(hidden_size=256, num_heads=2))  # head_dim 128 not covered yet
+
+
+def test_plugin_install_on_module_standin():
+    """install() on an object shaped like InternVLChatModel (vision_model + mlp1 modules) rebinds extract_feature."""
+    import types
+    from aigv_assessor_b200 import plugin
+
+    cfg = tiny()
+    sd = synth.make_weights(cfg, seed=9)
+
+    class VM(torch.nn.Module):
+        pass
+
+    vm = VM()
+    vm.config = types.SimpleNamespace(hidden_size=cfg.hidden_size, num_attention_heads=cfg.num_heads,
+                                      intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_layers,
+                                      image_size=cfg.image_size, patch_size=cfg.patch_size, qkv_bias=True,
+                                      qk_normalization=False, norm_type="layer_norm", layer_norm_eps=1e-6)
+    vsd = {k[len("vision_model."):]: torch.from_numpy(v).cuda() for k, v in sd.items() if k.startswith("vision_model.")}
+    vm.state_dict = lambda: vsd
+    W, C = cfg.shuffled_width, cfg.llm_hidden
+    mlp1 = torch.nn.Sequential(torch.nn.LayerNorm(W), torch.nn.Linear(W, C), torch.nn.GELU(), torch.nn.Linear(C, C))
+    mlp1.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in sd.items() if k.startswith("mlp1.")})
+
+    class Model:
+        select_layer, downsample_ratio, ps_version = -1, 0.5, "v2"
+
+        def extract_feature(self, pixel_values):  # 4-D variant (internvl_chat/modeling_internvl_chat.py:390-409)
+            raise AssertionError("original path must not run")
+
+    m = Model()
+    m.vision_model, m.mlp1 = vm, mlp1.cuda().to(torch.bfloat16)
+    eng = plugin.install(m)
+    assert eng is not None
+    pv = _pv(2, cfg, 10)
+    y = m.extract_feature(pv)
+    assert y.shape == (2, 16, 16, C) and not y.requires_grad
+    ref = vo.extract_feature(pv.float().cpu().numpy(), sd, cfg)
+    assert vo.error_metrics(y.float().cpu().numpy().reshape(2, 256, C), ref)[0] < TOL
+    plugin.uninstall(m)
+    with pytest.raises(AssertionError):
+        m.extract_feature(pv)

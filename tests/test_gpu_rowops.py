@@ -1,0 +1,93 @@
+"""Row-wise kernels (norms, im2col, token assembly, pixel-shuffle+LN) vs the numpy oracle, through the C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+from aigv_assessor_b200 import _lib, synth
+from oracle import vit_oracle as vo
+from tests.gpu_util import dev, emax, ptr, stream
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,D,rms", [(1025, 1024, 0), (77, 128, 0), (300, 3200, 1), (64, 256, 1)])
+def test_norm(rows, D, rms):
+    rng = np.random.default_rng(rows + D)
+    x = (rng.standard_normal((rows, D)) * 2 + 0.5).astype(np.float32)
+    w = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(D)).astype(np.float32)
+    y = torch.empty((rows, D), dtype=torch.bfloat16, device="cuda")
+    lib = _lib.load()
+    st = lib.aigv_layernorm(ptr(dev(x)), ptr(dev(w)), None if rms else ptr(dev(b)), ptr(y), rows, D, 1e-6, rms,
+                            stream())
+    assert st == 0
+    torch.cuda.synchronize()
+    ref = vo.rms_norm(x, w, 1e-6) if rms else vo.layer_norm(x, w, b, 1e-6)
+    got = y.float().cpu().numpy()
+    assert emax(got, ref) < 4e-3
+
+
+def test_rmsnorm_inplace_on_column_block():
+    rows, D = 200, 256
+    rng = np.random.default_rng(3)
+    x = synth.bf16_round(rng.standard_normal((rows, 3 * D)).astype(np.float32))
+    w = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    t = dev(x, torch.bfloat16)
+    lib = _lib.load()
+    assert lib.aigv_rmsnorm_inplace(ptr(t), ptr(dev(w)), rows, D, 3 * D, D, 1e-6, stream()) == 0
+    torch.cuda.synchronize()
+    got = t.float().cpu().numpy()
+    ref = x.copy()
+    ref[:, D:2 * D] = vo.rms_norm(x[:, D:2 * D], w, 1e-6)
+    assert np.array_equal(got[:, :D], x[:, :D]) and np.array_equal(got[:, 2 * D:], x[:, 2 * D:])
+    assert emax(got, ref) < 4e-3
+
+
+def test_im2col_and_assemble_equal_oracle_embeddings():
+    from aigv_assessor_b200.config import tiny
+    from tests.gpu_util import gemm
+    cfg = tiny()
+    sd = synth.make_weights(cfg, seed=5)
+    pv = synth.make_pixel_values(2, cfg, seed=6)
+    n, D, P, kp = 2, cfg.hidden_size, cfg.num_patches, 640
+    lib = _lib.load()
+    patches = torch.empty((n * P, kp), dtype=torch.bfloat16, device="cuda")
+    assert lib.aigv_im2col(ptr(dev(pv, torch.bfloat16)), ptr(patches), n, cfg.image_size, cfg.patch_size, kp,
+                           stream()) == 0
+    torch.cuda.synchronize()
+    # bit-exact gather check against the oracle's patch flattening
+    g, ps = cfg.grid, cfg.patch_size
+    ref_p = pv.reshape(n, 3, g, ps, g, ps).transpose(0, 2, 4, 1, 3, 5).reshape(n * P, 588)
+    got_p = patches.float().cpu().numpy()
+    assert np.array_equal(got_p[:, :588], ref_p) and not got_p[:, 588:].any()
+    w = np.zeros((D, kp), np.float32)
+    w[:, :588] = sd["vision_model.embeddings.patch_embedding.weight"].reshape(D, 588)
+    pe = gemm(patches, dev(w, torch.bfloat16), bias=dev(sd["vision_model.embeddings.patch_embedding.bias"]),
+              out_dtype=torch.float32)
+    x = torch.empty((n, P + 1, D), dtype=torch.float32, device="cuda")
+    assert lib.aigv_assemble_tokens(ptr(pe), ptr(dev(sd["vision_model.embeddings.class_embedding"].reshape(-1))),
+                                    ptr(dev(sd["vision_model.embeddings.position_embedding"].reshape(-1, D))), ptr(x),
+                                    n, P, D, stream()) == 0
+    torch.cuda.synchronize()
+    ref = vo.embeddings(pv, sd, cfg)
+    assert emax(x.cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("apply_ln", [0, 1])
+def test_pixel_shuffle_ln(apply_ln):
+    n, g, D = 2, 32, 128
+    rng = np.random.default_rng(8)
+    x = synth.bf16_round(rng.standard_normal((n, g * g + 1, D)).astype(np.float32))
+    w = (1 + 0.1 * rng.standard_normal(4 * D)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(4 * D)).astype(np.float32)
+    y = torch.empty((n * 256, 4 * D), dtype=torch.bfloat16, device="cuda")
+    lib = _lib.load()
+    assert lib.aigv_pixel_shuffle(ptr(dev(x)), ptr(dev(w)), ptr(dev(b)), ptr(y), n, g, D, 1e-5, apply_ln,
+                                  stream()) == 0
+    torch.cuda.synchronize()
+    ref = vo.pixel_shuffle(x[:, 1:].reshape(n, g, g, D), 0.5, "v2").reshape(n * 256, 4 * D)
+    got = y.float().cpu().numpy()
+    if apply_ln:
+        assert emax(got, vo.layer_norm(ref, w, b, 1e-5)) < 4e-3
+    else:
+        assert np.array_equal(got, ref)  # pure data movement: bit exact

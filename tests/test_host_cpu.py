@@ -1,0 +1,116 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every declared symbol, host logic, gloo sharding."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from aigv_assessor_b200 import _lib, config, sharding, synth, tiling
+from oracle import preprocess_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "aigv_b200.h")).read()
+    declared = set(re.findall(r"\b(aigv_[a-z0-9_]+)\s*\(", header))
+    declared -= {"aigv_handle"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.aigv_version()
+    assert lib.aigv_status_string(-5) == b"unsupported configuration"
+
+
+def test_library_contains_blackwell_sass():
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out and "UTMALDG" in out and "LDTM" in out  # tcgen05.mma, TMA load, tcgen05.ld
+    assert "HMMA.16816" not in out  # no legacy mma.sync path
+
+
+def test_tile_grid_matches_oracle_and_c_abi():
+    lib = _lib.load()
+    for (w, h) in [(1280, 720), (1920, 1080), (720, 1280), (768, 512), (448, 448), (512, 512), (100, 1000), (333, 777)]:
+        for mx in (1, 6, 12):
+            ref = po.tile_grid(w, h, 1, mx, 448)
+            assert tuple(tiling.tile_grid(w, h, 1, mx, 448)) == tuple(ref)
+            gi, gj = C.c_int(), C.c_int()
+            assert lib.aigv_tile_grid(w, h, 1, mx, 448, C.byref(gi), C.byref(gj)) == 0
+            assert (gi.value, gj.value) == tuple(ref)
+    assert tiling.tiles_per_frame(1280, 720, 6) == 3 and tiling.tiles_per_frame(768, 512, 6) == 7
+    assert tiling.tiles_per_frame(1280, 720, 1) == 1
+    assert lib.aigv_tile_grid(0, 10, 1, 6, 448, C.byref(gi), C.byref(gj)) == -1
+
+
+def test_flops_per_frame_matches_survey():
+    assert abs(config.internvit_300m(4096).flops_per_frame() / 1e9 - 740.773) < 0.01
+    assert abs(config.internvit_300m(2048).flops_per_frame() / 1e9 - 730.035) < 0.01
+
+
+def test_synth_is_bf16_exact_and_seeded():
+    cfg = config.tiny()
+    a, b = synth.make_weights(cfg, 5), synth.make_weights(cfg, 5)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    w = a["mlp1.1.weight"]
+    assert np.array_equal(synth.from_bf16_bits(synth.to_bf16_bits(w)), w)
+    assert np.array_equal(synth.to_bf16_bits(w), torch.from_numpy(w).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))
+
+
+def test_merge_lora_names():
+    from aigv_assessor_b200.engine import merge_lora_names
+    w, a, b = torch.randn(6, 4), torch.randn(2, 4), torch.randn(6, 2)
+    sd = {"base_model.model.encoder.layers.0.attn.qkv.base_layer.weight": w,
+          "base_model.model.encoder.layers.0.attn.qkv.lora_A.default.weight": a,
+          "base_model.model.encoder.layers.0.attn.qkv.lora_B.default.weight": b,
+          "base_model.model.encoder.layers.0.ls1": torch.ones(4)}
+    out = merge_lora_names(sd)
+    assert set(out) == {"encoder.layers.0.attn.qkv.weight", "encoder.layers.0.ls1"}
+    assert torch.allclose(out["encoder.layers.0.attn.qkv.weight"], w + 2.0 * b @ a)
+
+
+def test_engine_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from aigv_assessor_b200.engine import VisionEngine
+    with pytest.raises(_lib.AigvError):
+        VisionEngine(config.tiny())
+
+
+def test_shard_indices_cover_everything_once():
+    for n in (0, 1, 7, 32):
+        for w in (1, 2, 8):
+            got = sorted(i for r in range(w) for i in sharding.shard_indices(n, r, w))
+            assert got == list(range(n))
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from aigv_assessor_b200 import sharding
+dist.init_process_group("gloo", init_method="env://")
+r, w = dist.get_rank(), dist.get_world_size()
+for n in (5, 4, 1):
+    idx = sharding.shard_indices(n, r, w)
+    local = torch.stack([torch.full((3,), float(i)) for i in idx]) if idx else torch.empty((0, 3))
+    full = sharding.gather_clip_results(local, n)
+    assert full.shape == (n, 3) and torch.equal(full[:, 0], torch.arange(n, dtype=torch.float32)), (r, n, full)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_gather_clip_results_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
