@@ -22,7 +22,8 @@ def test_attention_matches_reference(frames, S, H):
     qkv = (torch.randn((frames * S, 3 * H * d), generator=g) * 1.5).to(torch.bfloat16)
     out = torch.full((frames * S, H * d), float("nan"), dtype=torch.bfloat16, device="cuda")
     lib = _lib.load()
-    st = lib.aigv_attention(ptr(dev(qkv)), ptr(out), frames, S, H, d, d ** -0.5, stream())
+    dq = dev(qkv)
+    st = lib.aigv_attention(ptr(dq), ptr(out), frames, S, H, d, d ** -0.5, stream())
     assert st == 0
     torch.cuda.synchronize()
     ref = _attn_ref(qkv, frames, S, H, d)
@@ -40,7 +41,8 @@ def test_attention_peaked_rows_are_stable():
     qkv = qkv.to(torch.bfloat16)
     out = torch.empty((S, d), dtype=torch.bfloat16, device="cuda")
     lib = _lib.load()
-    assert lib.aigv_attention(ptr(dev(qkv)), ptr(out), frames, S, H, d, d ** -0.5, stream()) == 0
+    dq = dev(qkv)
+    assert lib.aigv_attention(ptr(dq), ptr(out), frames, S, H, d, d ** -0.5, stream()) == 0
     torch.cuda.synchronize()
     ref = _attn_ref(qkv, frames, S, H, d)
     assert emax(out.float().cpu().numpy(), ref.cpu().numpy()) < 1e-2

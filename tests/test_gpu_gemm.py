@@ -32,7 +32,8 @@ def test_gemm_bias_bf16(M, N, K):
     torch.backends.cuda.matmul.allow_tf32 = False
     a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
     bias = torch.randn(N, generator=torch.Generator().manual_seed(3))
-    y = gemm(dev(a), dev(w), bias=dev(bias))
+    da, dw, db = dev(a), dev(w), dev(bias)
+    y = gemm(da, dw, bias=db)
     ref = _ref(a, w, bias)
     # bf16 output rounding: 2^-9 relative of the value; gate on normalised max error
     assert emax(y.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
@@ -42,7 +43,8 @@ def test_gemm_gelu_bf16():
     M, N, K = 2050, 4096, 1024
     a, w = _rand((M, K), 4), _rand((N, K), 5, K ** -0.5)
     bias = torch.randn(N, generator=torch.Generator().manual_seed(6))
-    y = gemm(dev(a), dev(w), bias=dev(bias), gelu=True)
+    da, dw, db = dev(a), dev(w), dev(bias)
+    y = gemm(da, dw, bias=db, gelu=True)
     ref = _ref(a, w, bias, gelu=True)
     assert emax(y.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
 
@@ -53,7 +55,8 @@ def test_gemm_scale_residual_f32_inplace():
     g = torch.Generator().manual_seed(9)
     bias, ls, res = torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g), torch.randn((M, N), generator=g)
     x = dev(res.clone())
-    gemm(dev(a), dev(w), bias=dev(bias), colscale=dev(ls), residual=x, out=x)  # in place, like the residual stream
+    da, dw, db, dl = dev(a), dev(w), dev(bias), dev(ls)
+    gemm(da, dw, bias=db, colscale=dl, residual=x, out=x)  # in place, like the residual stream
     ref = _ref(a, w, bias, ls, res)
     assert emax(x.cpu().numpy(), ref.cpu().numpy()) < 1e-4
 
@@ -64,7 +67,8 @@ def test_gemm_f32_exact_small_integers():
     g = torch.Generator().manual_seed(10)
     a = torch.randint(-4, 5, (M, K), generator=g).to(torch.bfloat16)
     w = torch.randint(-4, 5, (N, K), generator=g).to(torch.bfloat16)
-    y = gemm(dev(a), dev(w), out_dtype=torch.float32)
+    da, dw = dev(a), dev(w)
+    y = gemm(da, dw, out_dtype=torch.float32)
     ref = a.double() @ w.double().T
     assert np.array_equal(y.cpu().numpy().astype(np.float64), ref.numpy())
 

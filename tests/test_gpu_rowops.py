@@ -18,8 +18,8 @@ def test_norm(rows, D, rms):
     b = (0.1 * rng.standard_normal(D)).astype(np.float32)
     y = torch.empty((rows, D), dtype=torch.bfloat16, device="cuda")
     lib = _lib.load()
-    st = lib.aigv_layernorm(ptr(dev(x)), ptr(dev(w)), None if rms else ptr(dev(b)), ptr(y), rows, D, 1e-6, rms,
-                            stream())
+    dx, dw, db = dev(x), dev(w), dev(b)  # keep the device buffers alive until the kernel has run
+    st = lib.aigv_layernorm(ptr(dx), ptr(dw), None if rms else ptr(db), ptr(y), rows, D, 1e-6, rms, stream())
     assert st == 0
     torch.cuda.synchronize()
     ref = vo.rms_norm(x, w, 1e-6) if rms else vo.layer_norm(x, w, b, 1e-6)
@@ -32,9 +32,9 @@ def test_rmsnorm_inplace_on_column_block():
     rng = np.random.default_rng(3)
     x = synth.bf16_round(rng.standard_normal((rows, 3 * D)).astype(np.float32))
     w = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
-    t = dev(x, torch.bfloat16)
+    t, dw = dev(x, torch.bfloat16), dev(w)
     lib = _lib.load()
-    assert lib.aigv_rmsnorm_inplace(ptr(t), ptr(dev(w)), rows, D, 3 * D, D, 1e-6, stream()) == 0
+    assert lib.aigv_rmsnorm_inplace(ptr(t), ptr(dw), rows, D, 3 * D, D, 1e-6, stream()) == 0
     torch.cuda.synchronize()
     got = t.float().cpu().numpy()
     ref = x.copy()
@@ -52,8 +52,8 @@ def test_im2col_and_assemble_equal_oracle_embeddings():
     n, D, P, kp = 2, cfg.hidden_size, cfg.num_patches, 640
     lib = _lib.load()
     patches = torch.empty((n * P, kp), dtype=torch.bfloat16, device="cuda")
-    assert lib.aigv_im2col(ptr(dev(pv, torch.bfloat16)), ptr(patches), n, cfg.image_size, cfg.patch_size, kp,
-                           stream()) == 0
+    dpv = dev(pv, torch.bfloat16)
+    assert lib.aigv_im2col(ptr(dpv), ptr(patches), n, cfg.image_size, cfg.patch_size, kp, stream()) == 0
     torch.cuda.synchronize()
     # bit-exact gather check against the oracle's patch flattening
     g, ps = cfg.grid, cfg.patch_size
@@ -65,9 +65,9 @@ def test_im2col_and_assemble_equal_oracle_embeddings():
     pe = gemm(patches, dev(w, torch.bfloat16), bias=dev(sd["vision_model.embeddings.patch_embedding.bias"]),
               out_dtype=torch.float32)
     x = torch.empty((n, P + 1, D), dtype=torch.float32, device="cuda")
-    assert lib.aigv_assemble_tokens(ptr(pe), ptr(dev(sd["vision_model.embeddings.class_embedding"].reshape(-1))),
-                                    ptr(dev(sd["vision_model.embeddings.position_embedding"].reshape(-1, D))), ptr(x),
-                                    n, P, D, stream()) == 0
+    dcls = dev(sd["vision_model.embeddings.class_embedding"].reshape(-1))
+    dpos = dev(sd["vision_model.embeddings.position_embedding"].reshape(-1, D))
+    assert lib.aigv_assemble_tokens(ptr(pe), ptr(dcls), ptr(dpos), ptr(x), n, P, D, stream()) == 0
     torch.cuda.synchronize()
     ref = vo.embeddings(pv, sd, cfg)
     assert emax(x.cpu().numpy(), ref) < 1e-5
@@ -82,8 +82,8 @@ def test_pixel_shuffle_ln(apply_ln):
     b = (0.1 * rng.standard_normal(4 * D)).astype(np.float32)
     y = torch.empty((n * 256, 4 * D), dtype=torch.bfloat16, device="cuda")
     lib = _lib.load()
-    assert lib.aigv_pixel_shuffle(ptr(dev(x)), ptr(dev(w)), ptr(dev(b)), ptr(y), n, g, D, 1e-5, apply_ln,
-                                  stream()) == 0
+    dx, dw, db = dev(x), dev(w), dev(b)
+    assert lib.aigv_pixel_shuffle(ptr(dx), ptr(dw), ptr(db), ptr(y), n, g, D, 1e-5, apply_ln, stream()) == 0
     torch.cuda.synchronize()
     ref = vo.pixel_shuffle(x[:, 1:].reshape(n, g, g, D), 0.5, "v2").reshape(n * 256, 4 * D)
     got = y.float().cpu().numpy()

@@ -87,3 +87,17 @@ def test_normalize_lut_is_the_transform():
     pv = po.transform(tile)
     for c in range(3):
         assert np.array_equal(pv[c, 0], lut[c])
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_rms"])
+def test_torch_oracle_matches_reference_goldens(golden_dir, golden_meta, name):
+    import torch
+    from oracle import vit_oracle_torch as vt
+    cfg, g, sd, pv = _case(golden_dir, golden_meta, name)
+    out, vit = vt.extract_feature(torch.from_numpy(pv), vt.to_torch(sd), cfg, return_vit=True)
+    if name == "tiny":
+        assert vo.error_metrics(vit.numpy(), g["vit_out"])[0] < 1e-5
+        assert vo.error_metrics(out.numpy(), g["out"])[0] < 1e-5
+    else:
+        assert vo.error_metrics(vit.numpy()[:, ::41, ::16], g["vit_out_s"])[0] < 1e-5
+        assert vo.error_metrics(out.numpy()[:, ::8, ::16], g["out_s"])[0] < 1e-5
