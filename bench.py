@@ -43,7 +43,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or
                  k.startswith("nvmlClocksThrottleReason")}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -71,10 +71,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         reasons = sorted(r for r in self.reasons if r not in ("None", "GpuIdle", "All"))
