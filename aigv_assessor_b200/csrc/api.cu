@@ -33,17 +33,20 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                      uint32_t box_cols) {
+int make_tmap_2d(CUtensorMap* out, const void* base, int f32, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return -1;
-    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0 || box_cols * 2 != 128 || box_rows > 256)
+    const uint64_t esz = f32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * esz) % 16 != 0 || box_cols * esz != 128 ||
+        box_rows > 256)
         return -2;
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {ld * 2};
+    cuuint64_t gstride[1] = {ld * esz};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estride[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+    CUresult r = fn(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(base), gdim, gstride, box, estride,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -3;
@@ -104,7 +107,8 @@ struct LayerW {
 
 struct ActMaps {
     int n = -1;
-    CUtensorMap patches, xn, attn, h, ps, m1, qkv_full, qkv_tail;
+    CUtensorMap patches, xn, attn, h, ps, m1, qkv_full, qkv_tail;   // TMA loads (GEMM A operands, attention)
+    CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out;              // TMA stores / reduce-adds (GEMM outputs)
 };
 
 enum KClass { K_IM2COL = 0, K_GEMM_PATCH, K_ASSEMBLE, K_NORM, K_GEMM_QKV, K_QKNORM, K_ATTENTION, K_GEMM_PROJ,
@@ -215,6 +219,12 @@ int build_act_maps(aigv_handle* h, int n) {
     r |= make_tmap_bf16_2d(&h->maps.m1, h->m1, Mo, h->C, h->C, ba, bc);
     r |= make_tmap_bf16_2d(&h->maps.qkv_full, h->qkv, M, 3 * h->D, 3 * h->D, 128, 64);
     r |= make_tmap_bf16_2d(&h->maps.qkv_tail, h->qkv, M, 3 * h->D, 3 * h->D, attention_tail_rows(h->S), 64);
+    const int cr = gemm_box_rows_c(), cb = gemm_box_cols_c(false), cf = gemm_box_cols_c(true);
+    r |= make_tmap_2d(&h->maps.pe_out, h->pe, 1, Mp, h->D, h->D, cr, cf);
+    r |= make_tmap_2d(&h->maps.x_out, h->x, 1, M, h->D, h->D, cr, cf);
+    r |= make_tmap_2d(&h->maps.qkv_out, h->qkv, 0, M, 3 * h->D, 3 * h->D, cr, cb);
+    r |= make_tmap_2d(&h->maps.h_out, h->hbuf, 0, M, h->I, h->I, cr, cb);
+    r |= make_tmap_2d(&h->maps.m1_out, h->m1, 0, Mo, h->C, h->C, cr, cb);
     if (r) return -1;
     h->maps.n = n;
     return 0;
@@ -520,8 +530,9 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
     AIGV_LAUNCH(K_IM2COL, launch_im2col(pv, h->patches, n, h->cfg.image_size, h->cfg.patch_size, h->kpad, st), "im2col");
     {
         GemmEpilogue ep;
-        ep.bias = h->pe_b; ep.out_f32 = h->pe; ep.ld_out = D;
-        AIGV_LAUNCH(K_GEMM_PATCH, launch_gemm(h->maps.patches, h->tm_pe_w, Mp, D, h->kpad, ep, h->num_sms, st), "patch-embed gemm");
+        ep.bias = h->pe_b; ep.out_f32 = 1;
+        AIGV_LAUNCH(K_GEMM_PATCH, launch_gemm(h->maps.patches, h->tm_pe_w, h->maps.pe_out, Mp, D, h->kpad, ep, h->num_sms, st),
+                    "patch-embed gemm");
     }
     AIGV_LAUNCH(K_ASSEMBLE, launch_assemble_tokens(h->pe, h->cls, h->pos, h->x, n, h->P, D, st), "assemble tokens");
 
@@ -531,8 +542,9 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n1w, rms ? nullptr : w.n1b, h->xn, M, D, eps, rms, st), "norm1");
         {
             GemmEpilogue ep;
-            ep.bias = h->cfg.qkv_bias ? w.qkv_b : nullptr; ep.out_bf16 = h->qkv; ep.ld_out = 3 * D;
-            AIGV_LAUNCH(K_GEMM_QKV, launch_gemm(h->maps.xn, w.tm_qkv, M, 3 * D, D, ep, h->num_sms, st), "qkv gemm");
+            ep.bias = h->cfg.qkv_bias ? w.qkv_b : nullptr;
+            AIGV_LAUNCH(K_GEMM_QKV, launch_gemm(h->maps.xn, w.tm_qkv, h->maps.qkv_out, M, 3 * D, D, ep, h->num_sms, st),
+                        "qkv gemm");
         }
         if (h->cfg.qk_normalization) {
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st), "q_norm");
@@ -542,20 +554,23 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
                  "attention");
         {
             GemmEpilogue ep;
-            ep.bias = w.proj_b; ep.colscale = w.ls1; ep.residual = h->x; ep.ld_res = D; ep.out_f32 = h->x; ep.ld_out = D;
-            AIGV_LAUNCH(K_GEMM_PROJ, launch_gemm(h->maps.attn, w.tm_proj, M, D, D, ep, h->num_sms, st), "proj gemm");
+            ep.bias = w.proj_b; ep.colscale = w.ls1; ep.out_f32 = 1; ep.accumulate = 1;  // x += ls1 * (attn W^T + b)
+            AIGV_LAUNCH(K_GEMM_PROJ, launch_gemm(h->maps.attn, w.tm_proj, h->maps.x_out, M, D, D, ep, h->num_sms, st),
+                        "proj gemm");
         }
         // V2 norm2 -> V6 fc1+GELU -> V7 fc2 * ls2 + residual
         AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n2w, rms ? nullptr : w.n2b, h->xn, M, D, eps, rms, st), "norm2");
         {
             GemmEpilogue ep;
-            ep.bias = w.fc1_b; ep.gelu = 1; ep.out_bf16 = h->hbuf; ep.ld_out = I;
-            AIGV_LAUNCH(K_GEMM_FC1, launch_gemm(h->maps.xn, w.tm_fc1, M, I, D, ep, h->num_sms, st), "fc1 gemm");
+            ep.bias = w.fc1_b; ep.gelu = 1;
+            AIGV_LAUNCH(K_GEMM_FC1, launch_gemm(h->maps.xn, w.tm_fc1, h->maps.h_out, M, I, D, ep, h->num_sms, st),
+                        "fc1 gemm");
         }
         {
             GemmEpilogue ep;
-            ep.bias = w.fc2_b; ep.colscale = w.ls2; ep.residual = h->x; ep.ld_res = D; ep.out_f32 = h->x; ep.ld_out = D;
-            AIGV_LAUNCH(K_GEMM_FC2, launch_gemm(h->maps.h, w.tm_fc2, M, D, I, ep, h->num_sms, st), "fc2 gemm");
+            ep.bias = w.fc2_b; ep.colscale = w.ls2; ep.out_f32 = 1; ep.accumulate = 1;  // x += ls2 * (h W^T + b)
+            AIGV_LAUNCH(K_GEMM_FC2, launch_gemm(h->maps.h, w.tm_fc2, h->maps.x_out, M, D, I, ep, h->num_sms, st),
+                        "fc2 gemm");
         }
     }
     // X1/X2 + mlp1[0]: drop cls, pixel shuffle, LayerNorm(4D) ; X3: mlp1[1]+GELU, mlp1[3]
@@ -563,13 +578,18 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
              "pixel_shuffle+ln");
     {
         GemmEpilogue ep;
-        ep.bias = h->m1_b; ep.gelu = 1; ep.out_bf16 = h->m1; ep.ld_out = C;
-        AIGV_LAUNCH(K_GEMM_MLP1_A, launch_gemm(h->maps.ps, h->tm_m1_w, Mo, C, h->W4, ep, h->num_sms, st), "mlp1.1 gemm");
+        ep.bias = h->m1_b; ep.gelu = 1;
+        AIGV_LAUNCH(K_GEMM_MLP1_A, launch_gemm(h->maps.ps, h->tm_m1_w, h->maps.m1_out, Mo, C, h->W4, ep, h->num_sms, st),
+                    "mlp1.1 gemm");
     }
     {
         GemmEpilogue ep;
-        ep.bias = h->m2_b; ep.out_bf16 = out; ep.ld_out = C;
-        AIGV_LAUNCH(K_GEMM_MLP1_B, launch_gemm(h->maps.m1, h->tm_m2_w, Mo, C, C, ep, h->num_sms, st), "mlp1.3 gemm");
+        CUtensorMap tm_out;  // the caller's output tensor
+        if (make_tmap_2d(&tm_out, out, 0, Mo, C, C, gemm_box_rows_c(), gemm_box_cols_c(false)))
+            return fail(h, AIGV_ERR_INVALID, "output pointer must be 16-byte aligned");
+        ep.bias = h->m2_b;
+        AIGV_LAUNCH(K_GEMM_MLP1_B, launch_gemm(h->maps.m1, h->tm_m2_w, tm_out, Mo, C, C, ep, h->num_sms, st),
+                    "mlp1.3 gemm");
     }
     return AIGV_OK;
 }
@@ -719,13 +739,23 @@ int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias
                        const float* residual, float* out_f32, void* out_bf16, int M, int N, int K, int gelu,
                        void* stream) {
     if (!a_bf16 || !w_bf16 || M <= 0 || N <= 0 || K <= 0) return AIGV_ERR_INVALID;
-    CUtensorMap ta, tb;
+    if ((out_f32 != nullptr) == (out_bf16 != nullptr)) return AIGV_ERR_INVALID;
+    if (residual && !out_f32) return AIGV_ERR_INVALID;  // the residual stream is fp32
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUtensorMap ta, tb, tc;
     if (make_tmap_bf16_2d(&ta, a_bf16, M, K, K, gemm_box_rows_a(), gemm_box_cols())) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tb, w_bf16, N, K, K, gemm_box_rows_b(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    const bool f32 = out_f32 != nullptr;
+    if (make_tmap_2d(&tc, f32 ? (void*)out_f32 : out_bf16, f32, M, N, N, gemm_box_rows_c(), gemm_box_cols_c(f32)))
+        return AIGV_ERR_INVALID;
     GemmEpilogue ep;
-    ep.bias = bias; ep.colscale = colscale; ep.residual = residual; ep.ld_res = N;
-    ep.out_f32 = out_f32; ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); ep.ld_out = N; ep.gelu = gelu;
-    cudaError_t e = launch_gemm(ta, tb, M, N, K, ep, device_num_sms(), static_cast<cudaStream_t>(stream));
+    ep.bias = bias; ep.colscale = colscale; ep.out_f32 = f32; ep.gelu = gelu;
+    if (residual) {  // out = residual + ...: seed the output with the residual, then reduce-add (in place when aliased)
+        if (residual != out_f32)
+            AIGV_TRY0(cudaMemcpyAsync(out_f32, residual, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, st));
+        ep.accumulate = 1;
+    }
+    cudaError_t e = launch_gemm(ta, tb, tc, M, N, K, ep, device_num_sms(), st);
     if (e == cudaErrorInvalidValue) return AIGV_ERR_INVALID;
     return e == cudaSuccess ? AIGV_OK : AIGV_ERR_CUDA;
 }

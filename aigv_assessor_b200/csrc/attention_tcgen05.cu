@@ -177,67 +177,105 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
 #pragma unroll
         for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
 
+        // Warps whose 32 query rows are all beyond the sequence (only in the ragged last query block) skip the softmax
+        // math; they still take part in the barrier protocol so the MMA warp's schedule is unchanged.
+        const bool warp_live = q0 + warp * 32 < S;
+
         for (int j = 0; j < n_blocks; ++j) {
             const bool tail = j >= n_full;
             const int kv = tail ? tail_rows : BKV;
-            const int valid = tail ? tail_valid : BKV;
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            // pass 1: row maximum
-            float mx = -INFINITY;
-            for (int c = 0; c < kv; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tm_s + c, v);
-                tmem_ld_wait();
+            float alpha = 1.f;
+            if (warp_live) {
+                float mx = -INFINITY;
+                if (!tail) {
+                    // pass 1 (full block, no masking): row maximum
+#pragma unroll 1
+                    for (int c = 0; c < BKV; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tm_s + c, v);
+                        tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float s = __uint_as_float(v[i]);
-                    mx = fmaxf(mx, (c + i < valid) ? s : -INFINITY);
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    }
+                } else {
+                    for (int c = 0; c < kv; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tm_s + c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            mx = fmaxf(mx, (c + i < tail_valid) ? __uint_as_float(v[i]) : -INFINITY);
+                    }
                 }
+                const float m_new = fmaxf(m_run, mx);
+                alpha = ex2((m_run - m_new) * scale_log2);
+                const float m_scaled = m_new * scale_log2;
+                // pass 2: probabilities -> bf16 P tile in smem (swizzled K-major), row sum
+                float sum = 0.f;
+                auto emit = [&](const float (&p)[32], int c) {
+                    uint8_t* atom = p_row + (c >> 6) * TILE_BYTES;
+                    const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 w;
+                        w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
+                        w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
+                        w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
+                        w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
+                        *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) = w;
+                    }
+                };
+                if (!tail) {
+#pragma unroll 1
+                    for (int c = 0; c < BKV; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tm_s + c, v);
+                        tmem_ld_wait();
+                        float p[32];
+                        float part = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            p[i] = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
+                            part += p[i];
+                        }
+                        sum += part;
+                        emit(p, c);
+                    }
+                } else {
+                    for (int c = 0; c < kv; c += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tm_s + c, v);
+                        tmem_ld_wait();
+                        float p[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float e = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
+                            p[i] = (c + i < tail_valid) ? e : 0.f;
+                            sum += p[i];
+                        }
+                        emit(p, c);
+                    }
+                }
+                l_run = l_run * alpha + sum;
+                m_run = m_new;
+                fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = ex2((m_run - m_new) * scale_log2);
-            const float m_scaled = m_new * scale_log2;
-            // pass 2: probabilities -> bf16 P tile in smem (swizzled K-major), row sum
-            float sum = 0.f;
-            for (int c = 0; c < kv; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tm_s + c, v);
-                tmem_ld_wait();
-                float p[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float e = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
-                    p[i] = (c + i < valid) ? e : 0.f;
-                    sum += p[i];
-                }
-                uint8_t* atom = p_row + (c >> 6) * TILE_BYTES;
-                const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 w;
-                    w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
-                    w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
-                    w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
-                    w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
-                    *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) = w;
-                }
-            }
-            l_run = l_run * alpha + sum;
-            m_run = m_new;
-            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             tc_fence_before();
             mbar_arrive(p_full);
             // fold O_j
             mbar_wait(o_full, j & 1);
             tc_fence_after();
+            if (warp_live) {
 #pragma unroll
-            for (int c = 0; c < HD; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tm_o + c, v);
-                tmem_ld_wait();
+                for (int c = 0; c < HD; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tm_o + c, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], alpha, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], alpha, __uint_as_float(v[i]));
+                }
             }
             tc_fence_before();
             mbar_arrive(o_empty);

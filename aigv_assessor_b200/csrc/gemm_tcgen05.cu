@@ -1,7 +1,7 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogue.
 //
-//   C[M,N] = epilogue( A[M,K] (bf16, K contiguous)  x  W[N,K]^T (bf16, K contiguous, i.e. nn.Linear weight layout) )
-//   epilogue(acc) = residual + colscale * act(acc + bias)        (each term optional; fp32 math; bf16 or fp32 store)
+//   C[M,N] (op)= colscale * act( A[M,K] (bf16, K contiguous) x W[N,K]^T (bf16, nn.Linear weight layout) + bias )
+//   op is a TMA store (bf16 or fp32) or a TMA reduce-add into the fp32 residual stream (x += ...); fp32 math.
 //
 // Replaces the cuBLASLt GEMM + separate bias / GELU / layer-scale / residual kernels behind
 //   attn.qkv  (modeling_intern_vit.py:129,163)   attn.proj + *ls1 + residual (:141,175,224)
@@ -10,7 +10,8 @@
 //
 // Tile 128x256x64, 4-stage TMA->smem ring (128B swizzle), UMMA M=128 N=256 K=16 issued by one thread,
 // two 256-column fp32 accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Warps 0-7: epilogue (warp%4 = TMEM lane quadrant, warp/4 = column half); warp 8: TMA producer; warp 9: MMA issuer.
+// Warps 0-7: epilogue (warp%4 = TMEM lane quadrant, warp/4 = column half; results are staged through a 128B-swizzled
+// smem tile per warp and leave by TMA store / reduce-add); warp 8: TMA producer; warp 9: MMA issuer.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -24,15 +25,15 @@ constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + manual 1024B alignment slack
+constexpr int STG_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B (64 bf16 or 32 fp32 columns), 128B-swizzled
+constexpr int OFF_STG = STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr uint32_t TMEM_COLS = 512;
 
-template <bool kGelu, bool kOutF32>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, const GemmEpilogue& ep) {
-    const size_t off = static_cast<size_t>(row) * ep.ld_out + col0;
-    float x[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+// acc + bias -> act -> * colscale, on 32 consecutive columns starting at col0 (fp32 registers).
+template <bool kGelu>
+__device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep) {
     if (ep.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -51,39 +52,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
             x[j] *= s.x; x[j + 1] *= s.y; x[j + 2] *= s.z; x[j + 3] *= s.w;
         }
     }
-    if (ep.residual) {
-        const float* r = ep.residual + static_cast<size_t>(row) * ep.ld_res + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(r + j);
-            x[j] += t.x; x[j + 1] += t.y; x[j + 2] += t.z; x[j + 3] += t.w;
-        }
-    }
-    if (kOutF32) {
-        float* o = ep.out_f32 + off;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-    } else {
-        __nv_bfloat16* o = ep.out_bf16 + off;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            uint4 p;
-            p.x = pack_bf16x2(x[j], x[j + 1]);
-            p.y = pack_bf16x2(x[j + 2], x[j + 3]);
-            p.z = pack_bf16x2(x[j + 4], x[j + 5]);
-            p.w = pack_bf16x2(x[j + 6], x[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = p;
-        }
-    }
 }
 
 template <bool kGelu, bool kOutF32>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                    int K, GemmEpilogue ep) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpilogue ep) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -96,9 +72,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int num_k = (K + BK - 1) / BK;
     const int num_tiles = num_m * num_n;
 
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("aigv gemm: dynamic smem base not 1024B aligned\n");
+        __trap();
+    }
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
     }
     if (warp == 9) {
         if (lane == 0) {
@@ -171,23 +152,65 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ------------------------------------------------------------ epilogue warps
+        // TMEM -> registers (tcgen05.ld, lane == row) -> fp32 math -> 128B-swizzled smem staging tile -> TMA store
+        // (or TMA reduce-add into the fp32 residual stream): global traffic is fully coalesced and asynchronous.
         const int quad = warp & 3;
         const int half = warp >> 2;
+        uint8_t* stg = smem + OFF_STG + warp * STG_BYTES;
+        uint8_t* my_row = stg + lane * 128;
+        const int sw = lane & 7;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * BM + quad * 32 + lane;
+            const int row0 = m_blk * BM + quad * 32;
+            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * 128;
+            constexpr int CHUNK = kOutF32 ? 32 : 64;  // columns per staged tile (128 B per row)
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int coff = half * 128 + c * 32;
-                const int col0 = n_blk * BN + coff;
+            for (int c = 0; c < 128; c += CHUNK) {
+                const int col0 = n_blk * BN + half * 128 + c;
                 uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + coff, v);
+                float x[32];
+                uint4 packed[8];
+                tmem_ld_32x32(tm + c, v);
                 tmem_ld_wait();
-                if (row < M && col0 < N) epilogue_chunk<kGelu, kOutF32>(v, row, col0, ep);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                if (col0 < N) epilogue_math<kGelu>(x, col0, ep);
+                if (kOutF32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        packed[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                                               __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        packed[j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                               pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                    tmem_ld_32x32(tm + c + 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                    if (col0 + 32 < N) epilogue_math<kGelu>(x, col0 + 32, ep);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        packed[4 + j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                                   pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                }
+                // the previous TMA store of this warp must have finished reading the staging tile
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = packed[j];
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && row0 < M && col0 < N) {
+                    if (ep.accumulate) tma_reduce_add_2d(&tmC, stg, col0, row0);
+                    else tma_store_2d(&tmC, stg, col0, row0);
+                    tma_store_commit();
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -195,6 +218,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (lane == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -206,8 +230,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <bool kGelu, bool kOutF32>
-cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                           int num_sms, cudaStream_t stream) {
+cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                           const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
     auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32>;
     static bool configured = false;
     if (!configured) {
@@ -217,7 +241,7 @@ cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, int M
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, ep);
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, ep);
     return cudaGetLastError();
 }
 
@@ -227,17 +251,19 @@ int gemm_box_rows_a() { return BM; }
 int gemm_box_rows_b() { return BN; }
 int gemm_box_cols() { return BK; }
 
-cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                        int num_sms, cudaStream_t stream) {
+int gemm_box_rows_c() { return 32; }
+int gemm_box_cols_c(bool out_f32) { return out_f32 ? 32 : 64; }
+
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                        const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
-    if ((ep.out_f32 != nullptr) == (ep.out_bf16 != nullptr)) return cudaErrorInvalidValue;
-    const bool f32 = ep.out_f32 != nullptr;
+    if (ep.accumulate && !ep.out_f32) return cudaErrorInvalidValue;
     if (ep.gelu) {
-        return f32 ? launch_variant<true, true>(tmA, tmB, M, N, K, ep, num_sms, stream)
-                   : launch_variant<true, false>(tmA, tmB, M, N, K, ep, num_sms, stream);
+        return ep.out_f32 ? launch_variant<true, true>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream)
+                          : launch_variant<true, false>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream);
     }
-    return f32 ? launch_variant<false, true>(tmA, tmB, M, N, K, ep, num_sms, stream)
-               : launch_variant<false, false>(tmA, tmB, M, N, K, ep, num_sms, stream);
+    return ep.out_f32 ? launch_variant<false, true>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream)
+                      : launch_variant<false, false>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream);
 }
 
 }  // namespace aigv

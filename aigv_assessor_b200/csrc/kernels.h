@@ -11,26 +11,30 @@ namespace aigv {
 struct GemmEpilogue {
     const float* bias = nullptr;      // [N] fp32, optional
     const float* colscale = nullptr;  // [N] fp32, optional (layer scale ls1/ls2)
-    const float* residual = nullptr;  // [M, ld_res] fp32, optional (may alias out_f32: in-place residual stream)
-    float* out_f32 = nullptr;         // exactly one of out_f32 / out_bf16 is set
-    __nv_bfloat16* out_bf16 = nullptr;
-    int ld_out = 0;                   // elements
-    int ld_res = 0;
+    int out_f32 = 0;                  // output element type of the C tensor map: fp32 (1) or bf16 (0)
+    int accumulate = 0;               // fp32 only: C += result (TMA reduce-add; the in-place residual stream)
     int gelu = 0;                     // exact erf GELU after bias
 };
 
 // ---- TMA descriptors (host) -------------------------------------------------------------------------------------
-// Row-major bf16 matrix [rows, cols] with row stride `ld` elements; box = [box_rows, 64 cols], 128B swizzle.
-// Returns 0 on success.
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                      uint32_t box_cols);
+// Row-major matrix [rows, cols] (bf16, or fp32 when f32 != 0) with row stride `ld` elements; the box is
+// [box_rows, box_cols] with a 128-byte inner extent (64 bf16 / 32 fp32 columns), 128B swizzle. Returns 0 on success.
+int make_tmap_2d(CUtensorMap* out, const void* base, int f32, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols);
+inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows, uint32_t box_cols) {
+    return make_tmap_2d(out, base, 0, rows, cols, ld, box_rows, box_cols);
+}
 
 // ---- GEMM ------------------------------------------------------------------------------------------------------
 int gemm_box_rows_a();
 int gemm_box_rows_b();
 int gemm_box_cols();
-cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, const GemmEpilogue& ep,
-                        int num_sms, cudaStream_t stream);
+int gemm_box_rows_c();
+int gemm_box_cols_c(bool out_f32);
+// tmC: output map with box [gemm_box_rows_c(), gemm_box_cols_c(out_f32)].
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                        const GemmEpilogue& ep, int num_sms, cudaStream_t stream);
 
 // ---- attention -------------------------------------------------------------------------------------------------
 // qkv: bf16 [frames*S, 3*D] with channel order (three, head, d); out: bf16 [frames*S, D] (head-major channels).

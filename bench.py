@@ -294,9 +294,9 @@ def run_native(args, rank, local_rank, world):
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
-            fps, secs = cpu_oracle_fps(cfg, sd, args.cpu_sample_frames)
+            fps, secs = cpu_oracle_fps(cfg, sd, args.cpu_baseline_frames)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{args.cpu_sample_frames} frame(s) of the same workload through the torch-CPU "
+                                    "sample": f"{args.cpu_baseline_frames} frame(s) of the same workload through the torch-CPU "
                                               f"fp32 oracle port ({secs:.1f} s, {os.cpu_count()} threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -312,7 +312,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=64, help="tiles per GPU per step (8 clips of 8 frames)")
     ap.add_argument("--max-tiles", type=int, default=64, help="micro-batch the workspace is sized for")
-    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--cpu-sample-frames", type=int, default=2, help="--impl reference: frames per step")
+    ap.add_argument("--cpu-baseline-frames", type=int, default=16, help="native arm: frames timed on the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
