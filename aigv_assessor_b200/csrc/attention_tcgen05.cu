@@ -32,7 +32,7 @@ constexpr int OFF_K = OFF_Q + TILE_BYTES;
 constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
 constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
 constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int SMEM_BYTES = OFF_BAR + 256;  // 16 mbarriers + the TMEM base slot
 constexpr int THREADS = 192;
 constexpr uint32_t TMEM_COLS = 256;
 // TMEM: two 128-column buffers; buffer j%2 holds S_j and, once consumed, O_j in its first 64 columns.
