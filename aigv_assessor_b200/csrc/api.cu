@@ -107,7 +107,7 @@ struct LayerW {
 
 struct ActMaps {
     int n = -1;
-    CUtensorMap patches, xn, attn, h, ps, m1, qkv_full, qkv_tail;   // TMA loads (GEMM A operands, attention)
+    CUtensorMap patches, xn, attn, h, ps, m1, qkv_q, qkv_kv, qkv_tail;   // TMA loads (GEMM A operands, attention)
     CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out;              // TMA stores / reduce-adds (GEMM outputs)
 };
 
@@ -217,7 +217,8 @@ int build_act_maps(aigv_handle* h, int n) {
     r |= make_tmap_bf16_2d(&h->maps.h, h->hbuf, M, h->I, h->I, ba, bc);
     r |= make_tmap_bf16_2d(&h->maps.ps, h->ps, Mo, h->W4, h->W4, ba, bc);
     r |= make_tmap_bf16_2d(&h->maps.m1, h->m1, Mo, h->C, h->C, ba, bc);
-    r |= make_tmap_bf16_2d(&h->maps.qkv_full, h->qkv, M, 3 * h->D, 3 * h->D, 128, 64);
+    r |= make_tmap_bf16_2d(&h->maps.qkv_q, h->qkv, M, 3 * h->D, 3 * h->D, attention_q_rows(), 64);
+    r |= make_tmap_bf16_2d(&h->maps.qkv_kv, h->qkv, M, 3 * h->D, 3 * h->D, attention_kv_rows(), 64);
     r |= make_tmap_bf16_2d(&h->maps.qkv_tail, h->qkv, M, 3 * h->D, 3 * h->D, attention_tail_rows(h->S), 64);
     const int cr = gemm_box_rows_c(), cb = gemm_box_cols_c(false), cf = gemm_box_cols_c(true);
     r |= make_tmap_2d(&h->maps.pe_out, h->pe, 1, Mp, h->D, h->D, cr, cf);
@@ -550,7 +551,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st), "q_norm");
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.knw, M, D, 3 * D, D, eps, st), "k_norm");
         }
-        AIGV_LAUNCH(K_ATTENTION, launch_attention(h->maps.qkv_full, h->maps.qkv_tail, h->attn, n, S, h->H, h->hd, scale, st),
+        AIGV_LAUNCH(K_ATTENTION, launch_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->attn, n, S, h->H, h->hd, scale, st),
                  "attention");
         {
             GemmEpilogue ep;
@@ -765,10 +766,11 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
     if (!qkv_bf16 || !out_bf16 || frames <= 0 || S <= 0 || heads <= 0) return AIGV_ERR_INVALID;
     if (head_dim != 64) return AIGV_ERR_UNSUPPORTED;
     const uint64_t M = (uint64_t)frames * S, D3 = 3ull * heads * head_dim;
-    CUtensorMap tf, tt;
-    if (make_tmap_bf16_2d(&tf, qkv_bf16, M, D3, D3, 128, 64)) return AIGV_ERR_INVALID;
+    CUtensorMap tq, tk, tt;
+    if (make_tmap_bf16_2d(&tq, qkv_bf16, M, D3, D3, attention_q_rows(), 64)) return AIGV_ERR_INVALID;
+    if (make_tmap_bf16_2d(&tk, qkv_bf16, M, D3, D3, attention_kv_rows(), 64)) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tt, qkv_bf16, M, D3, D3, attention_tail_rows(S), 64)) return AIGV_ERR_INVALID;
-    AIGV_TRY0(launch_attention(tf, tt, static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
+    AIGV_TRY0(launch_attention(tq, tk, tt, static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
                                static_cast<cudaStream_t>(stream)));
     return AIGV_OK;
 }

@@ -6,15 +6,17 @@
 //
 // One CTA = one (frame, head, 128-query block). Q/K/V tiles are read straight out of the [M, 3D] QKV GEMM output by
 // TMA (no split / permute copies); channel order (three, head, d) as in modeling_intern_vit.py:164.
-//   warp 4: TMA producer (Q once; K and V double buffered)     warp 5: MMA issuer (one thread)
+//   warp 4: TMA producer (Q once; K and V double buffered, 64 keys per block)     warp 5: MMA issuer (one thread)
 //   warps 0-3: softmax, one query row per thread (TMEM lane == row, so row max / sum need no shuffles)
-// Per KV block j:  S = Q K_j^T (UMMA 128 x kv x 64 -> TMEM)  ->  online softmax in registers (exp2, scale*log2e folded)
-//   -> P_j (bf16) written to smem in the 128B-swizzled K-major layout  ->  O_j = P_j V_j (UMMA 128 x 64 x kv, V is the
-//   MN-major B operand exactly as TMA lands it)  ->  threads fold O_j into their fp32 register accumulator with the
-//   running rescale. S is double-buffered in TMEM (O_j reuses the dead S_j buffer), QK^T runs two blocks ahead and the
-//   O fold one block behind, so the softmax warps do not wait on the tensor core in steady state.
-//   S = 1025 = 8*128 + 1: the ragged tail is one short KV block (32 columns, 1 valid, rest masked).
-// Two CTAs are resident per SM (256 TMEM columns and ~112 KiB smem each) so one CTA's softmax overlaps the other's MMAs.
+// Per 64-key block j:  S = Q K_j^T (UMMA 128x64x64 -> TMEM cols [0,64))  ->  two passes over S from TMEM (row max, then
+//   p = exp2(s*scale*log2e - m_ref)) -> P_j (bf16) written to smem in the 128B-swizzled K-major layout ->
+//   O += P_j V_j (UMMA 128x64x64 accumulating in TMEM cols [64,128); V is the MN-major B operand exactly as TMA lands it).
+// O lives in TMEM for the whole KV loop. m_ref is a *stale* row maximum: it is only raised (and O, l rescaled through
+// tcgen05.ld/st) when the true running maximum exceeds it by more than 2^8, so p <= 256 always and the rescale is rare;
+// the final O / l is exact regardless of the reference point.
+// The kernel is MUFU(ex2)-bound, so residency matters more than tile size: 64 KiB smem, 128 TMEM columns and <=112
+// registers give 3 CTAs (12 softmax warps) per SM, which lets other CTAs' exp work hide each CTA's barrier round trips.
+// S = 1025 = 16*64 + 1: the ragged tail is one short KV block (32 columns, 1 valid, rest masked to -inf).
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -22,20 +24,23 @@ namespace aigv {
 
 namespace {
 
-constexpr int BQ = 128;        // query rows per CTA
-constexpr int BKV = 128;       // keys per full block
-constexpr int HD = 64;         // head dim
-constexpr int KV_STAGES = 2;
-constexpr int TILE_BYTES = BKV * HD * 2;  // 16 KiB (also the Q tile and one P atom)
+constexpr int BQ = 128;   // query rows per CTA
+constexpr int BKV = 64;   // keys per full block
+constexpr int HD = 64;    // head dim
+constexpr int Q_BYTES = BQ * HD * 2;    // 16 KiB
+constexpr int KV_BYTES = BKV * HD * 2;  // 8 KiB
+constexpr int P_BYTES = BQ * BKV * 2;   // 16 KiB (one 128B-swizzle atom column)
 constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + TILE_BYTES;
-constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
-constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;  // 16 mbarriers + the TMEM base slot
+constexpr int OFF_K = OFF_Q + Q_BYTES;        // 2 stages
+constexpr int OFF_V = OFF_K + 2 * KV_BYTES;   // 2 stages
+constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
+constexpr int OFF_BAR = OFF_P + P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;     // 11 mbarriers + the TMEM base slot
 constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
-// TMEM: two 128-column buffers; buffer j%2 holds S_j and, once consumed, O_j in its first 64 columns.
+constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t TM_S = 0;    // S block: columns [0,64)
+constexpr uint32_t TM_O = 64;   // O accumulator: columns [64,128)
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -43,9 +48,10 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_constant__ CUtensorMap tm_tail,
-                     __nv_bfloat16* __restrict__ out, int S, int D, int tail_rows, float scale_log2) {
+__global__ void __launch_bounds__(THREADS, 3)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                     const __grid_constant__ CUtensorMap tm_tail, __nv_bfloat16* __restrict__ out, int S, int D,
+                     int tail_rows, float scale_log2) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* q_full = bars + 0;
@@ -53,11 +59,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
     uint64_t* k_empty = bars + 3;   // [2]
     uint64_t* v_full = bars + 5;    // [2]
     uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;    // [2]  S_j landed in TMEM buffer j%2
-    uint64_t* o_full = bars + 11;   // [2]  O_j = P_j V_j landed in TMEM buffer j%2 (over the dead S_j)
-    uint64_t* o_empty = bars + 13;  // [2]  O_j folded into registers -> buffer j%2 may take S_{j+2}
-    uint64_t* p_full = bars + 15;   //      S_j consumed and P_j written to smem
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* s_full = bars + 9;    // S_j in TMEM (also: every earlier MMA, incl. P_{j-1} V_{j-1}, has completed)
+    uint64_t* p_full = bars + 10;   // S_j consumed, P_j written to smem, O rescaled if needed
+    uint64_t* o_done = bars + 11;   // last P V accumulated
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -74,7 +79,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
         __trap();
     }
     if (warp == 4 && lane == 0) {
-        tma_prefetch_desc(&tm_full);
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
         tma_prefetch_desc(&tm_tail);
     }
     if (warp == 5) {
@@ -85,11 +91,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
                 mbar_init(&k_empty[s], 1);
                 mbar_init(&v_full[s], 1);
                 mbar_init(&v_empty[s], 1);
-                mbar_init(&s_full[s], 1);
-                mbar_init(&o_full[s], 1);
-                mbar_init(&o_empty[s], BQ);
             }
+            mbar_init(s_full, 1);
             mbar_init(p_full, BQ);
+            mbar_init(o_done, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -104,119 +109,88 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
     if (warp == 4) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, TILE_BYTES);
-            tma_load_2d(smem + OFF_Q, &tm_full, q_full, head * HD, row_base + q0);
+            mbar_arrive_expect_tx(q_full, Q_BYTES);
+            tma_load_2d(smem + OFF_Q, &tm_q, q_full, head * HD, row_base + q0);
             for (int j = 0; j < n_blocks; ++j) {
                 const int st = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
                 const bool tail = j >= n_full;
-                const uint32_t bytes = tail ? tail_rows * HD * 2 : TILE_BYTES;
-                const CUtensorMap* tm = tail ? &tm_tail : &tm_full;
+                const uint32_t bytes = tail ? tail_rows * HD * 2 : KV_BYTES;
+                const CUtensorMap* tm = tail ? &tm_tail : &tm_kv;
                 const int r = row_base + j * BKV;
                 mbar_wait(&k_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&k_full[st], bytes);
-                tma_load_2d(smem + OFF_K + st * TILE_BYTES, tm, &k_full[st], D + head * HD, r);
+                tma_load_2d(smem + OFF_K + st * KV_BYTES, tm, &k_full[st], D + head * HD, r);
                 mbar_wait(&v_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&v_full[st], bytes);
-                tma_load_2d(smem + OFF_V + st * TILE_BYTES, tm, &v_full[st], 2 * D + head * HD, r);
+                tma_load_2d(smem + OFF_V + st * KV_BYTES, tm, &v_full[st], 2 * D + head * HD, r);
             }
         }
     } else if (warp == 5) {
         // ------------------------------------------------------------ MMA issuer
-        // S_j goes to TMEM buffer j%2; once the softmax warps have consumed it, O_j = P_j V_j is written over its first
-        // 64 columns; once O_j is folded, the buffer takes S_{j+2}. QK^T therefore runs two blocks ahead of the softmax
-        // and P V one block behind it, so the softmax warps never wait on the tensor core in steady state.
         if (lane == 0) {
             const uint32_t q_addr = smem_u32(smem + OFF_Q);
             const uint32_t p_addr = smem_u32(smem + OFF_P);
+            const uint32_t tm_s = tmem_base + TM_S;
+            const uint32_t tm_o = tmem_base + TM_O;
             auto issue_qk = [&](int j) {
                 const int st = j & 1;
                 const int kv = j >= n_full ? tail_rows : BKV;
                 mbar_wait(&k_full[st], (j >> 1) & 1);
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(smem + OFF_K + st * TILE_BYTES);
+                const uint32_t k_addr = smem_u32(smem + OFF_K + st * KV_BYTES);
                 const uint32_t idesc = umma_idesc_bf16(BQ, kv, 0, 0);
-                const uint32_t tm_s = tmem_base + st * BKV;
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) {
                     umma_bf16_ss(tm_s, umma_desc_sw128(q_addr + k * 32, 16, 1024),
                                  umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
                 }
-                umma_commit(&s_full[st]);
+                umma_commit(s_full);
                 umma_commit(&k_empty[st]);
             };
             mbar_wait(q_full, 0);
             issue_qk(0);
-            if (n_blocks > 1) issue_qk(1);
             for (int j = 0; j < n_blocks; ++j) {
                 const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
                 const int kv = j >= n_full ? tail_rows : BKV;
-                mbar_wait(p_full, j & 1);          // S_j consumed, P_j in smem
-                mbar_wait(&v_full[st], ph);
+                mbar_wait(p_full, j & 1);  // S_j consumed (buffer free), P_j in smem, O rescaled if it had to be
+                mbar_wait(&v_full[st], (j >> 1) & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + OFF_V + st * TILE_BYTES);
-                const uint32_t tm_o = tmem_base + st * BKV;
+                const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
                 constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major
                 for (int k = 0; k < kv / 16; ++k) {
-                    // A = P: K-major, two 64-column swizzle atoms of 16 KiB; B = V rows [16k, 16k+16): 2 KiB apart.
-                    const uint32_t pa = p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32;
-                    umma_bf16_ss(tm_o, umma_desc_sw128(pa, 16, 1024), umma_desc_sw128(v_addr + k * 2048, 16, 1024),
-                                 idesc_pv, k != 0 ? 1u : 0u);
+                    // A = P_j: K-major 128B-swizzled rows, 32 B per 16-key step; B = V rows [16k, 16k+16): 2 KiB apart.
+                    umma_bf16_ss(tm_o, umma_desc_sw128(p_addr + k * 32, 16, 1024),
+                                 umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(&o_full[st]);
                 umma_commit(&v_empty[st]);
-                if (j + 2 < n_blocks) {
-                    mbar_wait(&o_empty[st], ph);   // O_j folded -> buffer free for S_{j+2}
-                    issue_qk(j + 2);
-                }
+                if (j + 1 < n_blocks) issue_qk(j + 1);  // its s_full commit also covers P_j V_j
+                else umma_commit(o_done);
             }
         }
     } else {
         // ------------------------------------------------------------ softmax warps: one query row per thread
         const int r = threadIdx.x;  // 0..127 == TMEM lane
         const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const uint32_t tm_s = tm_lane + TM_S;
+        const uint32_t tm_o = tm_lane + TM_O;
         uint8_t* p_row = smem + OFF_P + r * 128;
         const int sw = r & 7;
-        float m_run = -INFINITY, l_run = 0.f;
-        float alpha_prev = 1.f;  // rescale that goes with the not-yet-folded O_{j-1}
-        float o_acc[HD];
-#pragma unroll
-        for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
+        float m_ref = -INFINITY;  // reference maximum, already multiplied by scale*log2e
+        float l_run = 0.f;
         // Warps whose 32 query rows are all beyond the sequence (only in the ragged last query block) skip the softmax
         // math; they still take part in the barrier protocol so the MMA warp's schedule is unchanged.
         const bool warp_live = q0 + warp * 32 < S;
 
-        auto fold = [&](int jj, float a) {  // o_acc = o_acc * a + O_jj
-            const int st = jj & 1;
-            mbar_wait(&o_full[st], (jj >> 1) & 1);
-            tc_fence_after();
-            if (warp_live) {
-#pragma unroll
-                for (int c = 0; c < HD; c += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tm_lane + st * BKV + c, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], a, __uint_as_float(v[i]));
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&o_empty[st]);
-        };
-
         for (int j = 0; j < n_blocks; ++j) {
             const bool tail = j >= n_full;
-            const int kv = tail ? tail_rows : BKV;
-            const uint32_t tm_s = tm_lane + (j & 1) * BKV;
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            mbar_wait(s_full, j & 1);
             tc_fence_after();
-            float alpha = 1.f, m_scaled = 0.f;
             if (warp_live) {
-                // pass 1: row maximum (four independent chains)
+                // pass 1: row maximum (independent chains)
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
                 if (!tail) {
-#pragma unroll 1
+#pragma unroll
                     for (int c = 0; c < BKV; c += 32) {
                         uint32_t v[32];
                         tmem_ld_32x32(tm_s + c, v);
@@ -230,7 +204,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
                         }
                     }
                 } else {
-                    for (int c = 0; c < kv; c += 32) {
+                    for (int c = 0; c < tail_rows; c += 32) {
                         uint32_t v[32];
                         tmem_ld_32x32(tm_s + c, v);
                         tmem_ld_wait();
@@ -239,20 +213,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
                             mx0 = fmaxf(mx0, (c + i < tail_valid) ? __uint_as_float(v[i]) : -INFINITY);
                     }
                 }
-                const float m_new = fmaxf(fmaxf(m_run, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
-                alpha = ex2((m_run - m_new) * scale_log2);
-                m_scaled = m_new * scale_log2;
-                m_run = m_new;
-            }
-            // fold the previous block's O (its P V ran while pass 1 was executing); frees P smem and the TMEM buffer
-            if (j > 0) fold(j - 1, alpha_prev);
-            alpha_prev = alpha;
-            if (warp_live) {
-                // pass 2: probabilities -> bf16 P tile in smem (swizzled K-major), row sum (four independent chains)
+                const float mxs = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+                const bool need = mxs > m_ref + RESCALE_THRESHOLD;  // always true for the first block (m_ref = -inf)
+                if (__any_sync(0xffffffffu, need)) {                 // warp-uniform: TMEM ops are warp-collective
+                    const float new_ref = need ? mxs : m_ref;
+                    if (j > 0) {
+                        // s_full(j) implies P_{j-1} V_{j-1} has completed, so O is quiescent: rescale it in place
+                        const float alpha = ex2(m_ref - new_ref);  // 1 for rows that keep their reference
+#pragma unroll
+                        for (int c = 0; c < HD; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tm_o + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                            tmem_st_32x32(tm_o + c, v);
+                        }
+                        tmem_st_wait();
+                        l_run *= alpha;
+                    }
+                    m_ref = new_ref;
+                }
+                // pass 2: probabilities -> bf16 P tile in smem (swizzled K-major), row sum (independent chains)
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 auto emit = [&](const float (&p)[32], int c) {
-                    uint8_t* atom = p_row + (c >> 6) * TILE_BYTES;
-                    const int chunk0 = (c & 63) >> 3;
+                    const int chunk0 = c >> 3;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint4 w;
@@ -260,11 +245,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
                         w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
                         w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
                         w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
-                        *reinterpret_cast<uint4*>(atom + (((chunk0 + q) ^ sw) << 4)) = w;
+                        *reinterpret_cast<uint4*>(p_row + (((chunk0 + q) ^ sw) << 4)) = w;
                     }
                 };
                 if (!tail) {
-#pragma unroll 1
+#pragma unroll
                     for (int c = 0; c < BKV; c += 32) {
                         uint32_t v[32];
                         tmem_ld_32x32(tm_s + c, v);
@@ -272,49 +257,58 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
                         float p[32];
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            p[i] = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
-                            p[i + 1] = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_scaled));
-                            p[i + 2] = ex2(fmaf(__uint_as_float(v[i + 2]), scale_log2, -m_scaled));
-                            p[i + 3] = ex2(fmaf(__uint_as_float(v[i + 3]), scale_log2, -m_scaled));
+                            p[i] = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+                            p[i + 1] = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
+                            p[i + 2] = ex2(fmaf(__uint_as_float(v[i + 2]), scale_log2, -m_ref));
+                            p[i + 3] = ex2(fmaf(__uint_as_float(v[i + 3]), scale_log2, -m_ref));
                             s0 += p[i]; s1 += p[i + 1]; s2 += p[i + 2]; s3 += p[i + 3];
                         }
                         emit(p, c);
                     }
                 } else {
-                    for (int c = 0; c < kv; c += 32) {
+                    for (int c = 0; c < tail_rows; c += 32) {
                         uint32_t v[32];
                         tmem_ld_32x32(tm_s + c, v);
                         tmem_ld_wait();
                         float p[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const float e = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
+                            const float e = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
                             p[i] = (c + i < tail_valid) ? e : 0.f;
                             s0 += p[i];
                         }
                         emit(p, c);
                     }
                 }
-                l_run = l_run * alpha + ((s0 + s1) + (s2 + s3));
+                l_run += (s0 + s1) + (s2 + s3);
                 fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             }
             tc_fence_before();
             mbar_arrive(p_full);
         }
-        fold(n_blocks - 1, alpha_prev);
 
+        mbar_wait(o_done, 0);
+        tc_fence_after();
         const int q = q0 + r;
-        if (q < S) {
+        if (warp_live) {
             const float inv = 1.0f / l_run;
             __nv_bfloat16* o = out + static_cast<size_t>(row_base + q) * D + head * HD;
 #pragma unroll
-            for (int c = 0; c < HD; c += 8) {
-                uint4 w;
-                w.x = pack_bf16x2(o_acc[c + 0] * inv, o_acc[c + 1] * inv);
-                w.y = pack_bf16x2(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
-                w.z = pack_bf16x2(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
-                w.w = pack_bf16x2(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
-                *reinterpret_cast<uint4*>(o + c) = w;
+            for (int c = 0; c < HD; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tm_o + c, v);
+                tmem_ld_wait();
+                if (q < S) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 w;
+                        w.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv, __uint_as_float(v[i + 1]) * inv);
+                        w.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+                        w.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+                        w.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+                        *reinterpret_cast<uint4*>(o + c + i) = w;
+                    }
+                }
             }
         }
     }
@@ -329,13 +323,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid_c
 
 }  // namespace
 
+int attention_q_rows() { return BQ; }
+int attention_kv_rows() { return BKV; }
 int attention_tail_rows(int S) {
     const int t = S % BKV;
     return t == 0 ? 32 : ((t + 31) / 32) * 32;
 }
 
-cudaError_t launch_attention(const CUtensorMap& tm_full, const CUtensorMap& tm_tail, __nv_bfloat16* out, int frames,
-                             int S, int heads, int head_dim, float softmax_scale, cudaStream_t stream) {
+cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
+                             __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
+                             cudaStream_t stream) {
     if (head_dim != HD || frames <= 0 || S <= 0 || heads <= 0) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
@@ -346,7 +343,7 @@ cudaError_t launch_attention(const CUtensorMap& tm_full, const CUtensorMap& tm_t
     }
     dim3 grid((S + BQ - 1) / BQ, heads, frames);
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    attention_fwd_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tm_full, tm_tail, out, S, heads * head_dim,
+    attention_fwd_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tm_q, tm_kv, tm_tail, out, S, heads * head_dim,
                                                                 attention_tail_rows(S), scale_log2);
     return cudaGetLastError();
 }

@@ -38,10 +38,14 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 
 // ---- attention -------------------------------------------------------------------------------------------------
 // qkv: bf16 [frames*S, 3*D] with channel order (three, head, d); out: bf16 [frames*S, D] (head-major channels).
-// tm_full: box [128 rows, 64 cols]; tm_tail: box [attention_tail_rows(S), 64 cols] over the same qkv matrix.
+// Three maps over the same qkv matrix, boxes [attention_q_rows(), 64], [attention_kv_rows(), 64] and
+// [attention_tail_rows(S), 64].
+int attention_q_rows();
+int attention_kv_rows();
 int attention_tail_rows(int S);
-cudaError_t launch_attention(const CUtensorMap& tm_full, const CUtensorMap& tm_tail, __nv_bfloat16* out, int frames,
-                             int S, int heads, int head_dim, float softmax_scale, cudaStream_t stream);
+cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
+                             __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
+                             cudaStream_t stream);
 
 // ---- row-wise / bandwidth kernels --------------------------------------------------------------------------------
 // y[r,:] = LN(x[r,:]) * w + b (b may be null -> RMSNorm when rms != 0). x fp32 [rows, D] -> y bf16 [rows, D].

@@ -48,6 +48,23 @@ def test_attention_peaked_rows_are_stable():
     assert emax(out.float().cpu().numpy(), ref.cpu().numpy()) < 1e-2
 
 
+def test_attention_monotone_scores_force_a_rescale_every_block():
+    # scores grow with the key index, so the running maximum overtakes the stale reference again and again
+    frames, S, H, d = 1, 1025, 2, 64
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn((S, H, d), generator=g) * 0.1 + 1.0
+    k = torch.randn((S, H, d), generator=g) * 0.1 + (torch.arange(S).float() / S * 6.0).view(S, 1, 1)
+    v = torch.randn((S, H, d), generator=g)
+    qkv = torch.stack([q, k, v], dim=1).reshape(S, 3 * H * d).to(torch.bfloat16)
+    out = torch.empty((S, H * d), dtype=torch.bfloat16, device="cuda")
+    lib = _lib.load()
+    dq = dev(qkv)
+    assert lib.aigv_attention(ptr(dq), ptr(out), frames, S, H, d, d ** -0.5, stream()) == 0
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, frames, S, H, d)
+    assert emax(out.float().cpu().numpy(), ref.cpu().numpy()) < 1e-2
+
+
 def test_attention_rejects_other_head_dims():
     lib = _lib.load()
     x = torch.zeros((128, 3 * 128), dtype=torch.bfloat16, device="cuda")
