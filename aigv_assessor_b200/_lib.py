@@ -42,7 +42,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into libaigv_b200.so (cross-compiles without a GPU)."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("AIGV_NVCC_EXTRA", "").split()  # experiments only, e.g. -DAIGV_ATTN_MIN_CTAS=3
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

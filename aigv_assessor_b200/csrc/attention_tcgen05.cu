@@ -8,8 +8,8 @@
 // TMA (no split / permute copies); channel order (three, head, d) as in modeling_intern_vit.py:164.
 //   warp 4: TMA producer (Q once; K and V double buffered, 64 keys per block)     warp 5: MMA issuer (one thread)
 //   warps 0-3: softmax, one query row per thread (TMEM lane == row, so row max / sum need no shuffles)
-// Per 64-key block j:  S = Q K_j^T (UMMA 128x64x64 -> TMEM cols [0,64))  ->  two passes over S from TMEM (row max, then
-//   p = exp2(s*scale*log2e - m_ref)) -> P_j (bf16) written to smem in the 128B-swizzled K-major layout ->
+// Per 64-key block j:  S = Q K_j^T (UMMA 128x64x64 -> TMEM cols [0,64))  ->  one tcgen05.ld pass pulls the 64-key row
+//   into registers (row max, p = exp2(s*scale*log2e - m_ref)) -> P_j (bf16) written to smem, 128B-swizzled K-major ->
 //   O += P_j V_j (UMMA 128x64x64 accumulating in TMEM cols [64,128); V is the MN-major B operand exactly as TMA lands it).
 // O lives in TMEM for the whole KV loop. m_ref is a *stale* row maximum: it is only raised (and O, l rescaled through
 // tcgen05.ld/st) when the true running maximum exceeds it by more than 2^8, so p <= 256 always and the rescale is rare;
@@ -48,7 +48,10 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(THREADS, 3)
+#ifndef AIGV_ATTN_MIN_CTAS
+#define AIGV_ATTN_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(THREADS, AIGV_ATTN_MIN_CTAS)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_tail, __nv_bfloat16* __restrict__ out, int S, int D,
                      int tail_rows, float scale_log2) {
@@ -187,31 +190,27 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             if (warp_live) {
-                // pass 1: row maximum (independent chains)
+                // Single pass over S: the whole 64-key row is pulled into registers once (TMEM reads, ~64 B/clk/SM, are
+                // as scarce as MUFU throughput here), then max -> (rare) rescale -> exp2 -> bf16 P tile.
+                const int ncol = tail ? tail_rows : BKV;
+                uint32_t va[32], vb[32];  // columns [0,32) and [32,64) of this thread's row
+                tmem_ld_32x32(tm_s, va);
+                if (ncol > 32) tmem_ld_32x32(tm_s + 32, vb);
+                tmem_ld_wait();
+                if (tail) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i >= tail_valid) va[i] = 0xff800000u;  // -inf: exp2 gives exactly 0
+                        if (i + 32 >= tail_valid) vb[i] = 0xff800000u;
+                    }
+                }
                 float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-                if (!tail) {
 #pragma unroll
-                    for (int c = 0; c < BKV; c += 32) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(tm_s + c, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-                            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-                            mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-                            mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
-                        }
-                    }
-                } else {
-                    for (int c = 0; c < tail_rows; c += 32) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(tm_s + c, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            mx0 = fmaxf(mx0, (c + i < tail_valid) ? __uint_as_float(v[i]) : -INFINITY);
-                    }
+                for (int i = 0; i < 32; i += 4) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
+                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(vb[i + 2])));
+                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(va[i + 3]), __uint_as_float(vb[i + 3])));
                 }
                 const float mxs = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
                 const bool need = mxs > m_ref + RESCALE_THRESHOLD;  // always true for the first block (m_ref = -inf)
@@ -220,65 +219,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     if (j > 0) {
                         // s_full(j) implies P_{j-1} V_{j-1} has completed, so O is quiescent: rescale it in place
                         const float alpha = ex2(m_ref - new_ref);  // 1 for rows that keep their reference
-#pragma unroll
+#pragma unroll 1
                         for (int c = 0; c < HD; c += 32) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(tm_o + c, v);
+                            uint32_t o[32];
+                            tmem_ld_32x32(tm_o + c, o);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                            tmem_st_32x32(tm_o + c, v);
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st_32x32(tm_o + c, o);
                         }
                         tmem_st_wait();
                         l_run *= alpha;
                     }
                     m_ref = new_ref;
                 }
-                // pass 2: probabilities -> bf16 P tile in smem (swizzled K-major), row sum (independent chains)
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                auto emit = [&](const float (&p)[32], int c) {
-                    const int chunk0 = c >> 3;
+                auto emit8 = [&](const uint32_t (&v)[32], int i0, int chunk) {
+                    float p[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 w;
-                        w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
-                        w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
-                        w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
-                        w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
-                        *reinterpret_cast<uint4*>(p_row + (((chunk0 + q) ^ sw) << 4)) = w;
-                    }
+                    for (int i = 0; i < 8; ++i) p[i] = ex2(fmaf(__uint_as_float(v[i0 + i]), scale_log2, -m_ref));
+                    s0 += p[0] + p[4]; s1 += p[1] + p[5]; s2 += p[2] + p[6]; s3 += p[3] + p[7];
+                    uint4 w;
+                    w.x = pack_bf16x2(p[0], p[1]);
+                    w.y = pack_bf16x2(p[2], p[3]);
+                    w.z = pack_bf16x2(p[4], p[5]);
+                    w.w = pack_bf16x2(p[6], p[7]);
+                    *reinterpret_cast<uint4*>(p_row + ((chunk ^ sw) << 4)) = w;
                 };
-                if (!tail) {
 #pragma unroll
-                    for (int c = 0; c < BKV; c += 32) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(tm_s + c, v);
-                        tmem_ld_wait();
-                        float p[32];
+                for (int c = 0; c < 4; ++c) emit8(va, 8 * c, c);
+                if (ncol > 32) {  // the tail block only carries tail_rows columns
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            p[i] = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
-                            p[i + 1] = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
-                            p[i + 2] = ex2(fmaf(__uint_as_float(v[i + 2]), scale_log2, -m_ref));
-                            p[i + 3] = ex2(fmaf(__uint_as_float(v[i + 3]), scale_log2, -m_ref));
-                            s0 += p[i]; s1 += p[i + 1]; s2 += p[i + 2]; s3 += p[i + 3];
-                        }
-                        emit(p, c);
-                    }
-                } else {
-                    for (int c = 0; c < tail_rows; c += 32) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(tm_s + c, v);
-                        tmem_ld_wait();
-                        float p[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float e = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
-                            p[i] = (c + i < tail_valid) ? e : 0.f;
-                            s0 += p[i];
-                        }
-                        emit(p, c);
-                    }
+                    for (int c = 0; c < 4; ++c) emit8(vb, 8 * c, 4 + c);
                 }
                 l_run += (s0 + s1) + (s2 + s3);
                 fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
