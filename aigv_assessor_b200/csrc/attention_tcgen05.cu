@@ -43,7 +43,7 @@ constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;          // KV_STAGES stages
 constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;     // KV_STAGES stages
 constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;     // TILES tiles x 2 buffers
 constexpr int OFF_BAR = OFF_P + TILES * 2 * P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 512;               // 1 + 4*KV_STAGES + 7*TILES mbarriers + the TMEM base slot
+constexpr int SMEM_BYTES = OFF_BAR + 512;               // 1 + 4*KV_STAGES + 8*TILES mbarriers + the TMEM base slot
 constexpr int SOFTMAX_WARPS = 4 * TILES;
 constexpr int THREADS = (SOFTMAX_WARPS + 2) * 32;
 constexpr uint32_t TMEM_COLS = 512;
@@ -69,8 +69,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint64_t* v_full = k_empty + KV_STAGES;      // [KV_STAGES]
     uint64_t* v_empty = v_full + KV_STAGES;      // [KV_STAGES]
     uint64_t* s_full = v_empty + KV_STAGES;      // [TILES][2]  S_j landed in TMEM buffer j%2
-    uint64_t* p_full = s_full + TILES * 2;       // [TILES]     S_j consumed, P_j in smem buffer j%2, O rescaled if needed
-    uint64_t* pv_done = p_full + TILES;          // [TILES][2]  P_j V_j accumulated -> P buffer j%2 free, O quiescent
+    // One p_full per S/P buffer: the softmax may finish blocks j and j+1 before the MMA thread observes block j, and a
+    // single barrier advancing two phases would alias the parity the MMA thread waits on.
+    uint64_t* p_full = s_full + TILES * 2;       // [TILES][2]  S_j consumed, P_j in smem buffer j%2, O rescaled if needed
+    uint64_t* pv_done = p_full + TILES * 2;      // [TILES][2]  P_j V_j accumulated -> P buffer j%2 free, O quiescent
     uint64_t* o_done = pv_done + TILES * 2;      // [TILES]     last P V accumulated
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + TILES);
 
@@ -108,7 +110,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 mbar_init(&s_full[2 * t + 1], 1);
                 mbar_init(&pv_done[2 * t], 1);
                 mbar_init(&pv_done[2 * t + 1], 1);
-                mbar_init(&p_full[t], BQ);
+                mbar_init(&p_full[2 * t], BQ);
+                mbar_init(&p_full[2 * t + 1], BQ);
                 mbar_init(&o_done[t], 1);
             }
             fence_mbar_init();
@@ -175,7 +178,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const int st = j % KV_STAGES;
                 const int kv = j >= n_full ? tail_rows : BKV;
                 for (int t = 0; t < n_tiles; ++t) {
-                    mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in smem, O(t) rescaled if it had to be
+                    // S_j(t) consumed, P_j(t) in smem, O(t) rescaled if it had to be
+                    mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1);
                     if (t == 0) mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
                     tc_fence_after();
                     const uint32_t p_addr = smem_u32(smem + OFF_P + (2 * t + (j & 1)) * P_BYTES);
@@ -286,7 +290,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 }
                 tc_fence_before();
-                mbar_arrive(&p_full[t]);
+                mbar_arrive(&p_full[2 * t + b]);
             }
 
             mbar_wait(&o_done[t], 0);
