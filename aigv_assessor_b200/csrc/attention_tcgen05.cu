@@ -127,10 +127,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
     if (warp == SOFTMAX_WARPS) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, n_tiles * Q_BYTES);
-            for (int t = 0; t < n_tiles; ++t)
-                tma_load_2d(smem + OFF_Q + t * Q_BYTES, &tm_q, q_full, head * HD, row_base + q0 + t * BQ);
+        // The whole warp runs the loop converged (so addresses/coordinates stay in uniform registers); one elected
+        // lane issues.
+        {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(q_full, n_tiles * Q_BYTES);
+                for (int t = 0; t < n_tiles; ++t)
+                    tma_load_2d(smem + OFF_Q + t * Q_BYTES, &tm_q, q_full, head * HD, row_base + q0 + t * BQ);
+            }
+            __syncwarp();
             for (int j = 0; j < n_blocks; ++j) {
                 const int st = j % KV_STAGES;
                 const uint32_t ph = (j / KV_STAGES) & 1;
@@ -139,11 +144,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const CUtensorMap* tm = tail ? &tm_tail : &tm_kv;
                 const int r = row_base + j * BKV;
                 mbar_wait(&k_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&k_full[st], bytes);
-                tma_load_2d(smem + OFF_K + st * KV_BYTES, tm, &k_full[st], D + head * HD, r);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&k_full[st], bytes);
+                    tma_load_2d(smem + OFF_K + st * KV_BYTES, tm, &k_full[st], D + head * HD, r);
+                }
+                __syncwarp();
                 mbar_wait(&v_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&v_full[st], bytes);
-                tma_load_2d(smem + OFF_V + st * KV_BYTES, tm, &v_full[st], 2 * D + head * HD, r);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&v_full[st], bytes);
+                    tma_load_2d(smem + OFF_V + st * KV_BYTES, tm, &v_full[st], 2 * D + head * HD, r);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == SOFTMAX_WARPS + 1) {
@@ -151,7 +162,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         // Prologue: S_0, S_1 of every tile. Then per block j and tile t (in order): wait P_j(t) -> O(t) += P_j V_j ->
         // S_{j+2}(t) = Q(t) K_{j+2}^T into the S buffer the softmax has just drained. A K/V stage is released by the
         // commit that follows its last reader (the last live tile).
-        if (lane == 0) {
+        // The whole warp runs the schedule converged and only the tcgen05 instructions are predicated on one elected
+        // lane: inside a divergent `if (lane == 0)` the compiler wraps every UTCHMMA in an ELECT/BRA.U.ANY loop with
+        // R2UR transfers (~20 dependent instructions per MMA), which made MMA *issue* the bottleneck of this kernel.
+        {
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             auto issue_qk = [&](int t, int j) {
                 const int st = j % KV_STAGES;
                 const int kv = j >= n_full ? tail_rows : BKV;
@@ -162,14 +177,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const uint32_t q_addr = smem_u32(smem + OFF_Q + t * Q_BYTES);
                 const uint32_t k_addr = smem_u32(smem + OFF_K + st * KV_BYTES);
                 const uint32_t idesc = umma_idesc_bf16(BQ, kv, 0, 0);
-                const uint32_t tm_s = tmem_base + t * TM_TILE + (j & 1) * BKV;
+                const uint32_t tm_s = tmem_u + t * TM_TILE + (j & 1) * BKV;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    umma_bf16_ss(tm_s, umma_desc_sw128(q_addr + k * 32, 16, 1024),
-                                 umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < HD / 16; ++k) {
+                        umma_bf16_ss(tm_s, umma_desc_sw128(q_addr + k * 32, 16, 1024),
+                                     umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&s_full[2 * t + (j & 1)]);
+                    if (t == n_tiles - 1) umma_commit(&k_empty[st]);
                 }
-                umma_commit(&s_full[2 * t + (j & 1)]);
-                if (t == n_tiles - 1) umma_commit(&k_empty[st]);
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             for (int j = 0; j < 2 && j < n_blocks; ++j)
@@ -184,16 +202,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     tc_fence_after();
                     const uint32_t p_addr = smem_u32(smem + OFF_P + (2 * t + (j & 1)) * P_BYTES);
                     const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
-                    const uint32_t tm_o = tmem_base + t * TM_TILE + TM_O;
+                    const uint32_t tm_o = tmem_u + t * TM_TILE + TM_O;
                     constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major
-                    for (int k = 0; k < kv / 16; ++k) {
-                        // A = P_j: K-major 128B-swizzled rows, 32 B per 16-key step; B = V rows [16k,16k+16): 2 KiB apart
-                        umma_bf16_ss(tm_o, umma_desc_sw128(p_addr + k * 32, 16, 1024),
-                                     umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+                    if (elect_one()) {
+                        for (int k = 0; k < kv / 16; ++k) {
+                            // A = P_j: K-major 128B-swizzled rows, 32 B per 16-key step; B = V rows [16k,16k+16): 2 KiB
+                            umma_bf16_ss(tm_o, umma_desc_sw128(p_addr + k * 32, 16, 1024),
+                                         umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_pv,
+                                         (j | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&pv_done[2 * t + (j & 1)]);
+                        if (t == n_tiles - 1) umma_commit(&v_empty[st]);
+                        if (j + 1 == n_blocks) umma_commit(&o_done[t]);
                     }
-                    umma_commit(&pv_done[2 * t + (j & 1)]);
-                    if (t == n_tiles - 1) umma_commit(&v_empty[st]);
-                    if (j + 1 == n_blocks) umma_commit(&o_done[t]);
+                    __syncwarp();
                     if (j + 2 < n_blocks) issue_qk(t, j + 2);
                 }
             }

@@ -104,38 +104,43 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 8) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / num_n, n_blk = tile % num_n;
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // (whole warp converged, one elected lane issues: keeps addresses/coordinates in uniform registers)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
                     tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 9) {
-        // ------------------------------------------------------------ MMA issuer (single thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ------------------------------------------------------------ MMA issuer
+        // The warp runs the loop converged and one elected lane issues the tcgen05 instructions; inside a divergent
+        // `if (lane == 0)` every UTCHMMA gets wrapped in an ELECT/BRA.U.ANY loop with R2UR transfers.
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_u + acc * BN;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + A_BYTES;
+                const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + A_BYTES;
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
@@ -143,12 +148,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
                 }
-                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
         }
     } else {
         // ------------------------------------------------------------ epilogue warps
