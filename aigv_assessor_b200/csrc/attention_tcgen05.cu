@@ -4,23 +4,21 @@
 // dropout 0, softmax_scale = d^-0.5) reached from InternAttention._flash_attn (modeling_intern_vit.py:162-177), and is
 // numerically the softmax(q*scale @ k^T) @ v of _naive_attn (modeling_intern_vit.py:143-157).
 //
-// One CTA (one per SM) = one (frame, head) x TWO 128-query tiles. Q/K/V tiles are read straight out of the [M, 3D] QKV
-// GEMM output by TMA (no split / permute copies); channel order (three, head, d) as in modeling_intern_vit.py:164. Both
-// query tiles consume every K/V stage, which halves the K/V tile traffic from L2 (measured to be the first bound of a
+// One CTA = one (frame, head) x TWO 128-query tiles. Q/K/V tiles are read straight out of the [M, 3D] QKV GEMM output
+// by TMA (no split / permute copies); channel order (three, head, d) as in modeling_intern_vit.py:164. Both query tiles
+// consume every K/V stage, which halves the K/V tile traffic from L2 (measured to be the first bound of a
 // one-tile-per-CTA kernel: ~5.9 TB/s of tile loads with the softmax math removed).
-//   warp 8: TMA producer (Q tiles once; K and V in 4-stage rings, 64 keys per block)   warp 9: MMA issuer (one thread)
+//   warp 8: TMA producer (Q tiles once; K and V double buffered, 64 keys per block)   warp 9: MMA issuer (one thread)
 //   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, one query row per thread (TMEM lane == row, so row max /
-//   sum need no shuffles).
-// Per tile and 64-key block j:  S_j = Q K_j^T (UMMA 128x64x64 -> TMEM buffer j%2)  ->  ONE tcgen05.ld pass pulls the row
-//   into registers: row max, p = exp2(s*scale*log2e - m_ref)  ->  P_j (bf16) to smem buffer j%2 in the 128B-swizzled
-//   K-major layout  ->  O += P_j V_j (UMMA 128x64x64 accumulating in TMEM; V is the MN-major B operand as TMA lands it).
-// Software pipeline: S and P are double buffered, so Q K^T runs two blocks ahead of the softmax and P V trails it; the
-// softmax warps never wait for the tensor core in steady state (the serial softmax -> barrier -> MMA -> barrier chain
-// of a single-buffered design measured ~2200 cycles per block, 4x the MMA time).
+//   sum need no shuffles). The two warpgroups ping-pong against the single MMA thread: while one does its exp work the
+//   tensor core runs the other's P V and next Q K^T.
+// Per tile and 64-key block j:  S = Q K_j^T (UMMA 128x64x64 -> TMEM)  ->  row max, p = exp2(s*scale*log2e - m_ref)
+//   -> P_j (bf16) to smem in the 128B-swizzled K-major layout  ->  O += P_j V_j (UMMA 128x64x64 accumulating in TMEM; V is
+//   the MN-major B operand exactly as TMA lands it).
 // O lives in TMEM for the whole KV loop. m_ref is a *stale* row maximum: it is only raised (and O, l rescaled through
-// tcgen05.ld/st, after waiting for the in-flight P V) when the true running maximum exceeds it by more than 2^8, so
-// p <= 256 always and the rescale is rare; the final O / l is exact regardless of the reference point.
-// Resources: 160 KiB smem, 512 TMEM columns (2 tiles x (2 S buffers + O)), 320 threads.
+// tcgen05.ld/st) when the true running maximum exceeds it by more than 2^8, so p <= 256 always and the rescale is rare;
+// the final O / l is exact regardless of the reference point.
+// Resources: 96 KiB smem, 256 TMEM columns, <=102 registers -> 2 CTAs (16 softmax warps) per SM.
 // S = 1025 = 16*64 + 1: the ragged tail is one short KV block (32 columns, 1 valid, rest masked to -inf); on the query
 // side the last CTA of a (frame, head) holds the single leftover row and skips its empty second tile entirely.
 #include "kernels.h"
@@ -34,21 +32,20 @@ constexpr int BQ = 128;    // query rows per tile
 constexpr int TILES = 2;   // query tiles per CTA
 constexpr int BKV = 64;    // keys per full block
 constexpr int HD = 64;     // head dim
-constexpr int KV_STAGES = 4;
 constexpr int Q_BYTES = BQ * HD * 2;    // 16 KiB
 constexpr int KV_BYTES = BKV * HD * 2;  // 8 KiB
 constexpr int P_BYTES = BQ * BKV * 2;   // 16 KiB (one 128B-swizzle atom column)
-constexpr int OFF_Q = 0;                                // TILES tiles
-constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;          // KV_STAGES stages
-constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;     // KV_STAGES stages
-constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;     // TILES tiles x 2 buffers
-constexpr int OFF_BAR = OFF_P + TILES * 2 * P_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 512;               // 1 + 4*KV_STAGES + 8*TILES mbarriers + the TMEM base slot
+constexpr int OFF_Q = 0;                            // TILES tiles
+constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;      // 2 stages
+constexpr int OFF_V = OFF_K + 2 * KV_BYTES;         // 2 stages
+constexpr int OFF_P = OFF_V + 2 * KV_BYTES;         // TILES tiles
+constexpr int OFF_BAR = OFF_P + TILES * P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;           // 15 mbarriers + the TMEM base slot
 constexpr int SOFTMAX_WARPS = 4 * TILES;
 constexpr int THREADS = (SOFTMAX_WARPS + 2) * 32;
-constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_TILE = 256;  // TMEM columns per query tile: S buffers at +0 and +64, O accumulator at +128
-constexpr uint32_t TM_O = 128;
+constexpr uint32_t TMEM_COLS = 128 * TILES;
+constexpr uint32_t TM_TILE = 128;  // TMEM columns per query tile: S block at +0 (64 cols), O accumulator at +64
+constexpr uint32_t TM_O = 64;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 __device__ __forceinline__ float ex2(float x) {
@@ -57,24 +54,21 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_tail, __nv_bfloat16* __restrict__ out, int S, int D,
                      int tail_rows, float scale_log2) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* q_full = bars;
-    uint64_t* k_full = q_full + 1;               // [KV_STAGES]
-    uint64_t* k_empty = k_full + KV_STAGES;      // [KV_STAGES]
-    uint64_t* v_full = k_empty + KV_STAGES;      // [KV_STAGES]
-    uint64_t* v_empty = v_full + KV_STAGES;      // [KV_STAGES]
-    uint64_t* s_full = v_empty + KV_STAGES;      // [TILES][2]  S_j landed in TMEM buffer j%2
-    // One p_full per S/P buffer: the softmax may finish blocks j and j+1 before the MMA thread observes block j, and a
-    // single barrier advancing two phases would alias the parity the MMA thread waits on.
-    uint64_t* p_full = s_full + TILES * 2;       // [TILES][2]  S_j consumed, P_j in smem buffer j%2, O rescaled if needed
-    uint64_t* pv_done = p_full + TILES * 2;      // [TILES][2]  P_j V_j accumulated -> P buffer j%2 free, O quiescent
-    uint64_t* o_done = pv_done + TILES * 2;      // [TILES]     last P V accumulated
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + TILES);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;    // [TILES] S_j in TMEM (also: every earlier MMA, incl. this tile's P_{j-1} V_{j-1}, done)
+    uint64_t* p_full = bars + 11;   // [TILES] S_j consumed, P_j written to smem, O rescaled if needed
+    uint64_t* o_done = bars + 13;   // [TILES] last P V accumulated
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -99,19 +93,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (warp == SOFTMAX_WARPS + 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int s = 0; s < KV_STAGES; ++s) {
+            for (int s = 0; s < 2; ++s) {
                 mbar_init(&k_full[s], 1);
                 mbar_init(&k_empty[s], 1);
                 mbar_init(&v_full[s], 1);
                 mbar_init(&v_empty[s], 1);
             }
             for (int t = 0; t < TILES; ++t) {
-                mbar_init(&s_full[2 * t], 1);
-                mbar_init(&s_full[2 * t + 1], 1);
-                mbar_init(&pv_done[2 * t], 1);
-                mbar_init(&pv_done[2 * t + 1], 1);
-                mbar_init(&p_full[2 * t], BQ);
-                mbar_init(&p_full[2 * t + 1], BQ);
+                mbar_init(&s_full[t], 1);
+                mbar_init(&p_full[t], BQ);
                 mbar_init(&o_done[t], 1);
             }
             fence_mbar_init();
@@ -127,8 +117,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
     if (warp == SOFTMAX_WARPS) {
         // ------------------------------------------------------------ TMA producer
-        // The whole warp runs the loop converged (so addresses/coordinates stay in uniform registers); one elected
-        // lane issues.
         {
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, n_tiles * Q_BYTES);
@@ -137,8 +125,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
             __syncwarp();
             for (int j = 0; j < n_blocks; ++j) {
-                const int st = j % KV_STAGES;
-                const uint32_t ph = (j / KV_STAGES) & 1;
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
                 const bool tail = j >= n_full;
                 const uint32_t bytes = tail ? tail_rows * HD * 2 : KV_BYTES;
                 const CUtensorMap* tm = tail ? &tm_tail : &tm_kv;
@@ -159,64 +147,57 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
     } else if (warp == SOFTMAX_WARPS + 1) {
         // ------------------------------------------------------------ MMA issuer
-        // Prologue: S_0, S_1 of every tile. Then per block j and tile t (in order): wait P_j(t) -> O(t) += P_j V_j ->
-        // S_{j+2}(t) = Q(t) K_{j+2}^T into the S buffer the softmax has just drained. A K/V stage is released by the
-        // commit that follows its last reader (the last live tile).
-        // The whole warp runs the schedule converged and only the tcgen05 instructions are predicated on one elected
-        // lane: inside a divergent `if (lane == 0)` the compiler wraps every UTCHMMA in an ELECT/BRA.U.ANY loop with
-        // R2UR transfers (~20 dependent instructions per MMA), which made MMA *issue* the bottleneck of this kernel.
+        // Per block j and tile t (in order): wait P_j(t) -> O(t) += P_j V_j -> S(t) = Q(t) K_{j+1}^T. A K/V stage is
+        // released by the commit that follows its last reader (the last live tile).
         {
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             auto issue_qk = [&](int t, int j) {
-                const int st = j % KV_STAGES;
+                const int st = j & 1;
                 const int kv = j >= n_full ? tail_rows : BKV;
                 if (t == 0) {
-                    mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+                    mbar_wait(&k_full[st], (j >> 1) & 1);
                     tc_fence_after();
                 }
                 const uint32_t q_addr = smem_u32(smem + OFF_Q + t * Q_BYTES);
                 const uint32_t k_addr = smem_u32(smem + OFF_K + st * KV_BYTES);
                 const uint32_t idesc = umma_idesc_bf16(BQ, kv, 0, 0);
-                const uint32_t tm_s = tmem_u + t * TM_TILE + (j & 1) * BKV;
+                const uint32_t tm_s = tmem_u + t * TM_TILE;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) {
                         umma_bf16_ss(tm_s, umma_desc_sw128(q_addr + k * 32, 16, 1024),
                                      umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
                     }
-                    umma_commit(&s_full[2 * t + (j & 1)]);
+                    umma_commit(&s_full[t]);
                     if (t == n_tiles - 1) umma_commit(&k_empty[st]);
                 }
                 __syncwarp();
             };
             mbar_wait(q_full, 0);
-            for (int j = 0; j < 2 && j < n_blocks; ++j)
-                for (int t = 0; t < n_tiles; ++t) issue_qk(t, j);
+            for (int t = 0; t < n_tiles; ++t) issue_qk(t, 0);
             for (int j = 0; j < n_blocks; ++j) {
-                const int st = j % KV_STAGES;
+                const int st = j & 1;
                 const int kv = j >= n_full ? tail_rows : BKV;
                 for (int t = 0; t < n_tiles; ++t) {
-                    // S_j(t) consumed, P_j(t) in smem, O(t) rescaled if it had to be
-                    mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1);
-                    if (t == 0) mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+                    mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in smem, O(t) rescaled if it had to be
+                    if (t == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t p_addr = smem_u32(smem + OFF_P + (2 * t + (j & 1)) * P_BYTES);
+                    const uint32_t p_addr = smem_u32(smem + OFF_P + t * P_BYTES);
                     const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
                     const uint32_t tm_o = tmem_u + t * TM_TILE + TM_O;
                     constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major
                     if (elect_one()) {
                         for (int k = 0; k < kv / 16; ++k) {
-                            // A = P_j: K-major 128B-swizzled rows, 32 B per 16-key step; B = V rows [16k,16k+16): 2 KiB
+                            // A = P_j: K-major 128B-swizzled rows, 32 B per 16-key step; B = V rows [16k,16k+16)
                             umma_bf16_ss(tm_o, umma_desc_sw128(p_addr + k * 32, 16, 1024),
                                          umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_pv,
                                          (j | k) != 0 ? 1u : 0u);
                         }
-                        umma_commit(&pv_done[2 * t + (j & 1)]);
                         if (t == n_tiles - 1) umma_commit(&v_empty[st]);
                         if (j + 1 == n_blocks) umma_commit(&o_done[t]);
                     }
                     __syncwarp();
-                    if (j + 2 < n_blocks) issue_qk(t, j + 2);
+                    if (j + 1 < n_blocks) issue_qk(t, j + 1);  // its s_full commit also covers P_j V_j of this tile
                 }
             }
         }
@@ -228,8 +209,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int tile_q0 = q0 + t * BQ;
         if (tile_q0 < S) {
             const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + t * TM_TILE;
+            const uint32_t tm_s = tm_lane;
             const uint32_t tm_o = tm_lane + TM_O;
-            uint8_t* p_tile = smem + OFF_P + 2 * t * P_BYTES + r * 128;
+            uint8_t* p_row = smem + OFF_P + t * P_BYTES + r * 128;
             const int sw = r & 7;
             float m_ref = -INFINITY;  // reference maximum, already multiplied by scale*log2e
             float l_run = 0.f;
@@ -239,80 +221,107 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
             for (int j = 0; j < n_blocks; ++j) {
                 const bool tail = j >= n_full;
-                const int b = j & 1;
-                mbar_wait(&s_full[2 * t + b], (j >> 1) & 1);
+                mbar_wait(&s_full[t], j & 1);
                 tc_fence_after();
                 if (warp_live) {
-                    const int ncol = tail ? tail_rows : BKV;
-                    uint32_t va[32], vb[32];  // columns [0,32) and [32,64) of this thread's row
-                    tmem_ld_32x32(tm_lane + b * BKV, va);
-                    if (ncol > 32) tmem_ld_32x32(tm_lane + b * BKV + 32, vb);
-                    tmem_ld_wait();
-                    if (tail) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (i >= tail_valid) va[i] = 0xff800000u;  // -inf: exp2 gives exactly 0
-                            if (i + 32 >= tail_valid) vb[i] = 0xff800000u;
-                        }
-                    }
+                    // pass 1: row maximum (independent chains)
                     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                    if (!tail) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
-                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 1]), __uint_as_float(vb[i + 1])));
-                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(vb[i + 2])));
-                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(va[i + 3]), __uint_as_float(vb[i + 3])));
+                        for (int c = 0; c < BKV; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tm_s + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+                                mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+                                mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
+                                mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
+                            }
+                        }
+                    } else {
+                        for (int c = 0; c < tail_rows; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tm_s + c, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                mx0 = fmaxf(mx0, (c + i < tail_valid) ? __uint_as_float(v[i]) : -INFINITY);
+                        }
                     }
                     const float mxs = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
                     const bool need = mxs > m_ref + RESCALE_THRESHOLD;  // always true for block 0 (m_ref = -inf)
                     if (__any_sync(0xffffffffu, need)) {                 // warp-uniform: TMEM ops are warp-collective
                         const float new_ref = need ? mxs : m_ref;
                         if (j > 0) {
-                            // O must be quiescent: wait for the in-flight P_{j-1} V_{j-1} (commits are cumulative)
-                            mbar_wait(&pv_done[2 * t + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
-                            tc_fence_after();
+                            // s_full(j) implies P_{j-1} V_{j-1} has completed, so O is quiescent: rescale it in place
                             const float alpha = ex2(m_ref - new_ref);  // 1 for rows that keep their reference
 #pragma unroll 1
                             for (int c = 0; c < HD; c += 32) {
-                                uint32_t o[32];
-                                tmem_ld_32x32(tm_o + c, o);
+                                uint32_t v[32];
+                                tmem_ld_32x32(tm_o + c, v);
                                 tmem_ld_wait();
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                                tmem_st_32x32(tm_o + c, o);
+                                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                                tmem_st_32x32(tm_o + c, v);
                             }
                             tmem_st_wait();
                             l_run *= alpha;
                         }
                         m_ref = new_ref;
                     }
+                    // pass 2: probabilities -> bf16 P tile in smem (swizzled K-major), row sum (independent chains)
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    uint4 w[8];
-                    auto exp8 = [&](const uint32_t (&v)[32], int i0) {
-                        float p[8];
+                    auto emit = [&](const float (&p)[32], int c) {
+                        const int chunk0 = c >> 3;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) p[i] = ex2(fmaf(__uint_as_float(v[i0 + i]), scale_log2, -m_ref));
-                        s0 += p[0] + p[4]; s1 += p[1] + p[5]; s2 += p[2] + p[6]; s3 += p[3] + p[7];
-                        return make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
-                                          pack_bf16x2(p[6], p[7]));
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 w;
+                            w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
+                            w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
+                            w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
+                            w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
+                            *reinterpret_cast<uint4*>(p_row + (((chunk0 + q) ^ sw) << 4)) = w;
+                        }
                     };
+                    if (!tail) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) w[c] = exp8(va, 8 * c);
-                    if (ncol > 32) {  // the tail block only carries tail_rows columns
+                        for (int c = 0; c < BKV; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tm_s + c, v);
+                            tmem_ld_wait();
+                            float p[32];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) w[4 + c] = exp8(vb, 8 * c);
+                            for (int i = 0; i < 32; i += 4) {
+                                p[i] = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+                                p[i + 1] = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
+                                p[i + 2] = ex2(fmaf(__uint_as_float(v[i + 2]), scale_log2, -m_ref));
+                                p[i + 3] = ex2(fmaf(__uint_as_float(v[i + 3]), scale_log2, -m_ref));
+                                s0 += p[i]; s1 += p[i + 1]; s2 += p[i + 2]; s3 += p[i + 3];
+                            }
+                            emit(p, c);
+                        }
+                    } else {
+                        for (int c = 0; c < tail_rows; c += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tm_s + c, v);
+                            tmem_ld_wait();
+                            float p[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float e = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+                                p[i] = (c + i < tail_valid) ? e : 0.f;
+                                s0 += p[i];
+                            }
+                            emit(p, c);
+                        }
                     }
                     l_run += (s0 + s1) + (s2 + s3);
-                    // P buffer b was last read by P_{j-2} V_{j-2}
-                    if (j >= 2) mbar_wait(&pv_done[2 * t + b], ((j - 2) >> 1) & 1);
-                    uint8_t* p_row = p_tile + b * P_BYTES;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c < 4 || ncol > 32) *reinterpret_cast<uint4*>(p_row + ((c ^ sw) << 4)) = w[c];
                     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 }
                 tc_fence_before();
-                mbar_arrive(&p_full[2 * t + b]);
+                mbar_arrive(&p_full[t]);
             }
 
             mbar_wait(&o_done[t], 0);
@@ -329,12 +338,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     if (q < S) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
-                            uint4 x;
-                            x.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv, __uint_as_float(v[i + 1]) * inv);
-                            x.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-                            x.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-                            x.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
-                            *reinterpret_cast<uint4*>(o + c + i) = x;
+                            uint4 w;
+                            w.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv, __uint_as_float(v[i + 1]) * inv);
+                            w.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+                            w.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+                            w.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+                            *reinterpret_cast<uint4*>(o + c + i) = w;
                         }
                     }
                 }
