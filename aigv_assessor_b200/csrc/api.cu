@@ -2,6 +2,7 @@
 // the frame front end and per-op test entry points. No torch types; nothing throws across the boundary.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -50,6 +51,21 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int f32, uint64_t rows, uin
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -3;
+}
+
+// Which GEMM kernel the path uses: the CTA-pair kernel (default) or the single-CTA one (AIGV_GEMM=1cta, bring-up aid).
+static bool gemm_use_pair() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AIGV_GEMM");
+        v = (e && strcmp(e, "1cta") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+static int w_box_rows() { return gemm_use_pair() ? gemm2_box_rows_b() : gemm_box_rows_b(); }
+static cudaError_t run_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
+                            const GemmEpilogue& ep, int num_sms, cudaStream_t st) {
+    return gemm_use_pair() ? launch_gemm2(a, b, c, M, N, K, ep, num_sms, st) : launch_gemm(a, b, c, M, N, K, ep, num_sms, st);
 }
 
 static int device_num_sms() {
@@ -465,7 +481,7 @@ int aigv_finalize_weights(aigv_handle* h, void* stream) {
     if (!h) return AIGV_ERR_INVALID;
     for (auto& kv : h->slots)
         if (kv.second.required && !kv.second.set) return fail(h, AIGV_ERR_MISSING, "weight not set: " + kv.first);
-    const int bb = gemm_box_rows_b(), bc = gemm_box_cols();
+    const int bb = w_box_rows(), bc = gemm_box_cols();
     int r = 0;
     r |= make_tmap_bf16_2d(&h->tm_pe_w, h->pe_w, h->D, h->kpad, h->kpad, bb, bc);
     r |= make_tmap_bf16_2d(&h->tm_m1_w, h->m1_w, h->C, h->W4, h->W4, bb, bc);
@@ -532,7 +548,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
     {
         GemmEpilogue ep;
         ep.bias = h->pe_b; ep.out_f32 = 1;
-        AIGV_LAUNCH(K_GEMM_PATCH, launch_gemm(h->maps.patches, h->tm_pe_w, h->maps.pe_out, Mp, D, h->kpad, ep, h->num_sms, st),
+        AIGV_LAUNCH(K_GEMM_PATCH, run_gemm(h->maps.patches, h->tm_pe_w, h->maps.pe_out, Mp, D, h->kpad, ep, h->num_sms, st),
                     "patch-embed gemm");
     }
     AIGV_LAUNCH(K_ASSEMBLE, launch_assemble_tokens(h->pe, h->cls, h->pos, h->x, n, h->P, D, st), "assemble tokens");
@@ -544,7 +560,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         {
             GemmEpilogue ep;
             ep.bias = h->cfg.qkv_bias ? w.qkv_b : nullptr;
-            AIGV_LAUNCH(K_GEMM_QKV, launch_gemm(h->maps.xn, w.tm_qkv, h->maps.qkv_out, M, 3 * D, D, ep, h->num_sms, st),
+            AIGV_LAUNCH(K_GEMM_QKV, run_gemm(h->maps.xn, w.tm_qkv, h->maps.qkv_out, M, 3 * D, D, ep, h->num_sms, st),
                         "qkv gemm");
         }
         if (h->cfg.qk_normalization) {
@@ -556,7 +572,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         {
             GemmEpilogue ep;
             ep.bias = w.proj_b; ep.colscale = w.ls1; ep.out_f32 = 1; ep.accumulate = 1;  // x += ls1 * (attn W^T + b)
-            AIGV_LAUNCH(K_GEMM_PROJ, launch_gemm(h->maps.attn, w.tm_proj, h->maps.x_out, M, D, D, ep, h->num_sms, st),
+            AIGV_LAUNCH(K_GEMM_PROJ, run_gemm(h->maps.attn, w.tm_proj, h->maps.x_out, M, D, D, ep, h->num_sms, st),
                         "proj gemm");
         }
         // V2 norm2 -> V6 fc1+GELU -> V7 fc2 * ls2 + residual
@@ -564,13 +580,13 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         {
             GemmEpilogue ep;
             ep.bias = w.fc1_b; ep.gelu = 1;
-            AIGV_LAUNCH(K_GEMM_FC1, launch_gemm(h->maps.xn, w.tm_fc1, h->maps.h_out, M, I, D, ep, h->num_sms, st),
+            AIGV_LAUNCH(K_GEMM_FC1, run_gemm(h->maps.xn, w.tm_fc1, h->maps.h_out, M, I, D, ep, h->num_sms, st),
                         "fc1 gemm");
         }
         {
             GemmEpilogue ep;
             ep.bias = w.fc2_b; ep.colscale = w.ls2; ep.out_f32 = 1; ep.accumulate = 1;  // x += ls2 * (h W^T + b)
-            AIGV_LAUNCH(K_GEMM_FC2, launch_gemm(h->maps.h, w.tm_fc2, h->maps.x_out, M, D, I, ep, h->num_sms, st),
+            AIGV_LAUNCH(K_GEMM_FC2, run_gemm(h->maps.h, w.tm_fc2, h->maps.x_out, M, D, I, ep, h->num_sms, st),
                         "fc2 gemm");
         }
     }
@@ -580,7 +596,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
     {
         GemmEpilogue ep;
         ep.bias = h->m1_b; ep.gelu = 1;
-        AIGV_LAUNCH(K_GEMM_MLP1_A, launch_gemm(h->maps.ps, h->tm_m1_w, h->maps.m1_out, Mo, C, h->W4, ep, h->num_sms, st),
+        AIGV_LAUNCH(K_GEMM_MLP1_A, run_gemm(h->maps.ps, h->tm_m1_w, h->maps.m1_out, Mo, C, h->W4, ep, h->num_sms, st),
                     "mlp1.1 gemm");
     }
     {
@@ -589,7 +605,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         if (make_tmap_2d(&tm_out, out, 0, Mo, C, C, gemm_box_rows_c(), gemm_box_cols_c(false)))
             return fail(h, AIGV_ERR_INVALID, "output pointer must be 16-byte aligned");
         ep.bias = h->m2_b;
-        AIGV_LAUNCH(K_GEMM_MLP1_B, launch_gemm(h->maps.m1, h->tm_m2_w, tm_out, Mo, C, C, ep, h->num_sms, st),
+        AIGV_LAUNCH(K_GEMM_MLP1_B, run_gemm(h->maps.m1, h->tm_m2_w, tm_out, Mo, C, C, ep, h->num_sms, st),
                     "mlp1.3 gemm");
     }
     return AIGV_OK;
@@ -745,7 +761,7 @@ int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUtensorMap ta, tb, tc;
     if (make_tmap_bf16_2d(&ta, a_bf16, M, K, K, gemm_box_rows_a(), gemm_box_cols())) return AIGV_ERR_INVALID;
-    if (make_tmap_bf16_2d(&tb, w_bf16, N, K, K, gemm_box_rows_b(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    if (make_tmap_bf16_2d(&tb, w_bf16, N, K, K, w_box_rows(), gemm_box_cols())) return AIGV_ERR_INVALID;
     const bool f32 = out_f32 != nullptr;
     if (make_tmap_2d(&tc, f32 ? (void*)out_f32 : out_bf16, f32, M, N, N, gemm_box_rows_c(), gemm_box_cols_c(f32)))
         return AIGV_ERR_INVALID;
@@ -756,7 +772,7 @@ int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias
             AIGV_TRY0(cudaMemcpyAsync(out_f32, residual, (size_t)M * N * 4, cudaMemcpyDeviceToDevice, st));
         ep.accumulate = 1;
     }
-    cudaError_t e = launch_gemm(ta, tb, tc, M, N, K, ep, device_num_sms(), st);
+    cudaError_t e = run_gemm(ta, tb, tc, M, N, K, ep, device_num_sms(), st);
     if (e == cudaErrorInvalidValue) return AIGV_ERR_INVALID;
     return e == cudaSuccess ? AIGV_OK : AIGV_ERR_CUDA;
 }

@@ -1,0 +1,274 @@
+// 2-CTA (cta_group::2) variant of the persistent tcgen05 GEMM: a CTA pair (cluster of 2, one TPC) owns a 256x256 output
+// tile; UMMA M=256 N=256 K=16 is issued by the leader CTA and each CTA stages only its own 128 rows of A and its own
+// 128 rows of W (half of N) per k-block: 32 KiB instead of 48 KiB of TMA fill + operand reads per 128x256x64 of MACs.
+// The 1-CTA kernel (gemm_tcgen05.cu) is shared-memory-bandwidth bound (~96 B/clk of operand reads + ~94 B/clk of TMA
+// fills against ~128 B/clk; measured 54-73% tensor-pipe active); the pair brings that to ~125 B/clk at full MMA rate.
+//
+// Same contract and epilogue as gemm_tcgen05.cu: C (op)= colscale * act(A W^T + bias), staged through 128B-swizzled smem
+// and written by TMA store / reduce-add.
+//   warp 8: TMA producer (each CTA loads its own operands; transaction bytes are credited to the LEADER's full barrier)
+//   warp 9: leader only: MMA issuer; commits are multicast to both CTAs' empty / accumulator-full barriers
+//   warps 0-7: epilogue of this CTA's 128 rows; they release the accumulator stage on the leader's barrier (remote arrive)
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace aigv {
+
+namespace {
+
+constexpr int BM = 128;          // rows per CTA (256 per pair)
+constexpr int BN = 256;          // columns per pair tile
+constexpr int BNH = 128;         // W rows staged per CTA
+constexpr int BK = 64, STAGES = 6, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_BYTES = BNH * BK * 2;  // 16 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int STG_BYTES = 4096;
+constexpr int OFF_STG = STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr uint32_t TMEM_COLS = 512;
+
+template <bool kGelu>
+__device__ __forceinline__ void epilogue_math2(float (&x)[32], int col0, const GemmEpilogue& ep) {
+    if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+        }
+    }
+    if (kGelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+    }
+    if (ep.colscale) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(ep.colscale + col0 + j));
+            x[j] *= s.x; x[j + 1] *= s.y; x[j + 2] *= s.z; x[j + 3] *= s.w;
+        }
+    }
+}
+
+template <bool kGelu, bool kOutF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpilogue ep) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();   // 0 = leader
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
+    const int num_n = (N + BN - 1) / BN;
+    const int num_k = (K + BK - 1) / BK;
+    const int num_tiles = num_m * num_n;
+
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("aigv gemm2: dynamic smem base not 1024B aligned\n");
+        __trap();
+    }
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+    }
+    if (warp == 9) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);    // leader: its own producer's arrive.expect_tx (bytes of BOTH CTAs)
+                mbar_init(&empty_bar[s], 1);   // multicast commit from the leader's MMA thread
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tfull_bar[s], 1);                // multicast commit
+                mbar_init(&tempty_bar[s], 2 * EPI_WARPS);   // leader: epilogue warps of both CTAs
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / TMA credit / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const int row_a = m_blk * 2 * BM + rank * BM;
+            const int row_b = n_blk * BN + rank * BNH;
+            for (int kb = 0; kb < num_k; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);
+                    tma_load_2d_pair(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, row_b);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 9) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_u + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+                            const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                            umma_bf16_ss_pair(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_pair(&empty_bar[stage], 3);                           // free the slot in both CTAs
+                        if (kb == num_k - 1) umma_commit_pair(&tfull_bar[acc], 3);        // accumulator -> both epilogues
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (this CTA's 128 rows)
+        const int quad = warp & 3;
+        const int half = warp >> 2;
+        uint8_t* stg = smem + OFF_STG + warp * STG_BYTES;
+        uint8_t* my_row = stg + lane * 128;
+        const int sw = lane & 7;
+        const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
+            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * 128;
+            constexpr int CHUNK = kOutF32 ? 32 : 64;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += CHUNK) {
+                const int col0 = n_blk * BN + half * 128 + c;
+                uint32_t v[32];
+                float x[32];
+                uint4 packed[8];
+                tmem_ld_32x32(tm + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                if (col0 < N) epilogue_math2<kGelu>(x, col0, ep);
+                if (kOutF32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        packed[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                                               __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        packed[j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                               pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                    tmem_ld_32x32(tm + c + 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                    if (col0 + 32 < N) epilogue_math2<kGelu>(x, col0 + 32, ep);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        packed[4 + j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                                   pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                }
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = packed[j];
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && row0 < M && col0 < N) {
+                    if (ep.accumulate) tma_reduce_add_2d(&tmC, stg, col0, row0);
+                    else tma_store_2d(&tmC, stg, col0, row0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (lane == 0) tma_store_wait<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers / TMEM
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <bool kGelu, bool kOutF32>
+cudaError_t launch_variant2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                            const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+    auto kern = gemm2_bf16_tn_kernel<kGelu, kOutF32>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    int pairs = num_sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    kern<<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, ep);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int gemm2_box_rows_a() { return BM; }
+int gemm2_box_rows_b() { return BNH; }
+
+cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                         const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
+    if (ep.accumulate && !ep.out_f32) return cudaErrorInvalidValue;
+    if (ep.gelu) {
+        return ep.out_f32 ? launch_variant2<true, true>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream)
+                          : launch_variant2<true, false>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream);
+    }
+    return ep.out_f32 ? launch_variant2<false, true>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream)
+                      : launch_variant2<false, false>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream);
+}
+
+}  // namespace aigv

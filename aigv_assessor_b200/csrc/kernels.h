@@ -36,6 +36,12 @@ int gemm_box_cols_c(bool out_f32);
 cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
                         const GemmEpilogue& ep, int num_sms, cudaStream_t stream);
 
+// 2-CTA (cta_group::2) variant: 256x256 tile per CTA pair; A box rows = gemm2_box_rows_a(), W box rows = gemm2_box_rows_b().
+int gemm2_box_rows_a();
+int gemm2_box_rows_b();
+cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                         const GemmEpilogue& ep, int num_sms, cudaStream_t stream);
+
 // ---- attention -------------------------------------------------------------------------------------------------
 // qkv: bf16 [frames*S, 3*D] with channel order (three, head, d); out: bf16 [frames*S, D] (head-major channels).
 // Three maps over the same qkv matrix, boxes [attention_q_rows(), 64], [attention_kv_rows(), 64] and
