@@ -49,6 +49,71 @@ __device__ __forceinline__ RowStats row_stats(SegPtr seg_ptr, int nseg, int seg_
     return {mean, rsqrtf(var + eps)};
 }
 
+// One warp per row, the whole row held in registers (VPL float4 per lane, D = 128 * VPL): a single global read per
+// element, all loads in flight at once, exact two-pass mean / variance in fp32, 16-byte bf16 stores.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+norm_f32_to_bf16_reg_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                            __nv_bfloat16* __restrict__ y, int rows, float eps, int rms) {
+    constexpr int D = 128 * VPL;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+    float4 v[VPL];
+    // lane owns float4 index (2*i)*32 + 2*lane + {0,1}: pairs of adjacent float4 -> one 16-byte bf16 store per pair
+    if constexpr (VPL == 1) {
+        v[0] = xr[lane];
+    } else {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) v[i] = xr[(i >> 1) * 64 + 2 * lane + (i & 1)];
+    }
+    float mean = 0.f;
+    if (!rms) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        mean = warp_sum(s) * (1.0f / D);
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    __nv_bfloat16* yr = y + static_cast<size_t>(row) * D;
+    auto nrm = [&](float xv, float wv, float bv) { return (xv - mean) * rstd * wv + bv; };
+    if constexpr (VPL >= 2) {
+#pragma unroll
+        for (int i = 0; i < VPL; i += 2) {
+            const int col = ((i >> 1) * 64 + 2 * lane) * 4;  // first of 8 consecutive columns
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + col));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + col + 4));
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (b) {
+                b0 = __ldg(reinterpret_cast<const float4*>(b + col));
+                b1 = __ldg(reinterpret_cast<const float4*>(b + col + 4));
+            }
+            uint4 o;
+            o.x = pack_bf16x2(nrm(v[i].x, w0.x, b0.x), nrm(v[i].y, w0.y, b0.y));
+            o.y = pack_bf16x2(nrm(v[i].z, w0.z, b0.z), nrm(v[i].w, w0.w, b0.w));
+            o.z = pack_bf16x2(nrm(v[i + 1].x, w1.x, b1.x), nrm(v[i + 1].y, w1.y, b1.y));
+            o.w = pack_bf16x2(nrm(v[i + 1].z, w1.z, b1.z), nrm(v[i + 1].w, w1.w, b1.w));
+            *reinterpret_cast<uint4*>(yr + col) = o;
+        }
+    } else {  // D = 128: one float4 per lane (the pair mapping degenerates to xr[lane] handled below)
+        const int col = lane * 4;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + col));
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b) b0 = __ldg(reinterpret_cast<const float4*>(b + col));
+        uint2 o;
+        o.x = pack_bf16x2(nrm(v[0].x, w0.x, b0.x), nrm(v[0].y, w0.y, b0.y));
+        o.y = pack_bf16x2(nrm(v[0].z, w0.z, b0.z), nrm(v[0].w, w0.w, b0.w));
+        *reinterpret_cast<uint2*>(yr + col) = o;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 norm_f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                         __nv_bfloat16* __restrict__ y, int rows, int D, float eps, int rms) {
@@ -207,7 +272,13 @@ inline int grid_for(size_t work_items, int threads, int cap = 148 * 16) {
 cudaError_t launch_norm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows, int D,
                                     float eps, int rms, cudaStream_t stream) {
     if (rows <= 0 || D <= 0 || (D % 8) != 0) return cudaErrorInvalidValue;
-    norm_f32_to_bf16_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, w, b, y, rows, D, eps, rms);
+    const int grid = (rows + 7) / 8;
+    switch (D) {
+        case 128: norm_f32_to_bf16_reg_kernel<1><<<grid, 256, 0, stream>>>(x, w, b, y, rows, eps, rms); break;
+        case 256: norm_f32_to_bf16_reg_kernel<2><<<grid, 256, 0, stream>>>(x, w, b, y, rows, eps, rms); break;
+        case 1024: norm_f32_to_bf16_reg_kernel<8><<<grid, 256, 0, stream>>>(x, w, b, y, rows, eps, rms); break;
+        default: norm_f32_to_bf16_kernel<<<grid, 256, 0, stream>>>(x, w, b, y, rows, D, eps, rms); break;
+    }
     return cudaGetLastError();
 }
 

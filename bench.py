@@ -221,22 +221,46 @@ def run_native(args, rank, local_rank, world):
     eng.profile(False)
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region ----------------------------------------------------
-    stage = torch.empty_like(devs[0])
-
-    def e2e_step(i):
-        stage.copy_(host[i % R], non_blocking=True)
-        out = step(stage)
-        out_host.copy_(out, non_blocking=True)
-
+    # The public API runs on the caller's stream, so a caller pipelines exactly like this: a copy-in stream, the
+    # compute stream and a copy-out stream, double buffered, chained with events. Every step still moves its own
+    # pixel_values host->device and its visual tokens device->host inside the timed region.
     ms_e2e = float("nan")
     if not args.no_e2e:
-        for i in range(min(args.warmup, 2)):
-            e2e_step(i)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        s_cmp = torch.cuda.current_stream()
+        stage = [torch.empty_like(devs[0]) for _ in range(2)]
+        outs = [None, None]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_run(n):
+            for b in range(2):
+                ev_free[b].record(s_cmp)
+                ev_copied[b].record(s_out)
+            for i in range(n):
+                b = i & 1
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_free[b])          # stage[b] no longer read by step i-2
+                    stage[b].copy_(host[i % R], non_blocking=True)
+                    ev_in[b].record(s_in)
+                s_cmp.wait_event(ev_in[b])
+                s_cmp.wait_event(ev_copied[b])           # outs[b] of step i-2 has left the device
+                outs[b] = step(stage[b])
+                ev_free[b].record(s_cmp)
+                ev_out[b].record(s_cmp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_out[b])
+                    out_host.copy_(outs[b], non_blocking=True)
+                    ev_copied[b].record(s_out)
+            s_cmp.wait_stream(s_out)
+
+        e2e_run(min(args.warmup, 2))
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for i in range(args.steps):
-            e2e_step(i)
+        e2e_run(args.steps)
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
