@@ -8,7 +8,9 @@
 // and written by TMA store / reduce-add.
 //   warp 8: TMA producer (each CTA loads its own operands; transaction bytes are credited to the LEADER's full barrier)
 //   warp 9: leader only: MMA issuer; commits are multicast to both CTAs' empty / accumulator-full barriers
-//   warps 0-7: epilogue of this CTA's 128 rows; they release the accumulator stage on the leader's barrier (remote arrive)
+//   warps 0-15: epilogue of this CTA's 128 rows (warp%4 = TMEM lane quadrant, warp/4 = 64-column slice; 4 warps per
+//   SMSP hide the GELU / TMEM-load latencies); they release the accumulator stage on the leader's barrier (remote arrive)
+//   warp 16: TMA producer, warp 17: MMA issuer
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -19,11 +21,11 @@ namespace {
 constexpr int BM = 128;          // rows per CTA (256 per pair)
 constexpr int BN = 256;          // columns per pair tile
 constexpr int BNH = 128;         // W rows staged per CTA
-constexpr int BK = 64, STAGES = 6, UMMA_K = 16;
+constexpr int BK = 64, STAGES = 5, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_BYTES = BNH * BK * 2;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;  // 4 per TMEM lane quadrant: each owns a 32-row x 64-column slice of the CTA's tile
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int STG_BYTES = 4096;
 constexpr int OFF_STG = STAGES * STAGE_BYTES;
@@ -78,12 +80,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         printf("aigv gemm2: dynamic smem base not 1024B aligned\n");
         __trap();
     }
-    if (warp == 8 && lane == 0) {
+    if (warp == EPI_WARPS && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
     }
-    if (warp == 9) {
+    if (warp == EPI_WARPS + 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&full_bar[s], 1);    // leader: its own producer's arrive.expect_tx (bytes of BOTH CTAs)
@@ -104,7 +106,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == EPI_WARPS) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
@@ -124,7 +126,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == EPI_WARPS + 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
         if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
@@ -162,7 +164,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // ------------------------------------------------------------ epilogue warps (this CTA's 128 rows)
         const int quad = warp & 3;
-        const int half = warp >> 2;
+        const int slice = warp >> 2;  // 64-column slice of the 256-column tile
         uint8_t* stg = smem + OFF_STG + warp * STG_BYTES;
         uint8_t* my_row = stg + lane * 128;
         const int sw = lane & 7;
@@ -175,40 +177,19 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
-            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * 128;
-            constexpr int CHUNK = kOutF32 ? 32 : 64;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += CHUNK) {
-                const int col0 = n_blk * BN + half * 128 + c;
+            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * 64;
+            const int colb = n_blk * BN + slice * 64;
+            // 32 accumulator columns -> bias / GELU / scale in fp32 (in place)
+            auto load32 = [&](int c, float (&x)[32]) {
                 uint32_t v[32];
-                float x[32];
-                uint4 packed[8];
                 tmem_ld_32x32(tm + c, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                if (col0 < N) epilogue_math2<kGelu>(x, col0, ep);
-                if (kOutF32) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        packed[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
-                                               __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        packed[j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                               pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
-                    tmem_ld_32x32(tm + c + 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                    if (col0 + 32 < N) epilogue_math2<kGelu>(x, col0 + 32, ep);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        packed[4 + j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                                   pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
-                }
-                if (lane == 0) tma_store_wait_read<0>();
+                if (colb + c < N) epilogue_math2<kGelu>(x, colb + c, ep);
+            };
+            auto flush = [&](const uint4 (&packed)[8], int col0) {
+                if (lane == 0) tma_store_wait_read<0>();  // previous TMA store has finished reading the staging tile
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = packed[j];
@@ -219,6 +200,32 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     else tma_store_2d(&tmC, stg, col0, row0);
                     tma_store_commit();
                 }
+            };
+            if (kOutF32) {
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 32) {  // two 32-column fp32 staging tiles (128 B rows)
+                    float x[32];
+                    uint4 packed[8];
+                    load32(c, x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        packed[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                                               __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+                    flush(packed, colb + c);
+                }
+            } else {
+                uint4 packed[8];  // one 64-column bf16 staging tile
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float x[32];
+                    load32(32 * h, x);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        packed[4 * h + j] =
+                            make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                       pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                }
+                flush(packed, colb);
             }
             tc_fence_before();
             __syncwarp();
@@ -231,7 +238,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     tc_fence_before();
     cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers / TMEM
-    if (warp == 9) {
+    if (warp == EPI_WARPS + 1) {
         tc_fence_after();
         tmem_dealloc_pair<TMEM_COLS>(tmem_base);
     }
