@@ -21,17 +21,26 @@ namespace {
 constexpr int BM = 128;          // rows per CTA (256 per pair)
 constexpr int BN = 256;          // columns per pair tile
 constexpr int BNH = 128;         // W rows staged per CTA
-constexpr int BK = 64, STAGES = 5, UMMA_K = 16;
+constexpr int BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_BYTES = BNH * BK * 2;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 16;  // 4 per TMEM lane quadrant: each owns a 32-row x 64-column slice of the CTA's tile
-constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int STG_BYTES = 4096;
-constexpr int OFF_STG = STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr uint32_t TMEM_COLS = 512;
+
+// Two shapes of the same kernel: the GELU epilogue is instruction-issue heavy and wants 16 epilogue warps (4 per SMSP)
+// at the price of one pipeline stage; the plain / residual epilogues are lighter and keep 8 warps and 6 stages.
+template <int kEpiWarps>
+struct Cfg {
+    static constexpr int EPI_WARPS = kEpiWarps;          // multiple of 4: warp%4 = TMEM lane quadrant
+    static constexpr int SLICES = kEpiWarps / 4;         // column slices of the 256-column tile
+    static constexpr int SLICE_COLS = BN / SLICES;       // 64 or 128 columns per warp
+    static constexpr int STAGES = kEpiWarps == 16 ? 5 : 6;
+    static constexpr int THREADS = (kEpiWarps + 2) * 32;
+    static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_STG + kEpiWarps * STG_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+};
 
 template <bool kGelu>
 __device__ __forceinline__ void epilogue_math2(float (&x)[32], int col0, const GemmEpilogue& ep) {
@@ -55,10 +64,12 @@ __device__ __forceinline__ void epilogue_math2(float (&x)[32], int col0, const G
     }
 }
 
-template <bool kGelu, bool kOutF32>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+template <bool kGelu, bool kOutF32, int kEpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<kEpiWarps>::THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpilogue ep) {
+    using C = Cfg<kEpiWarps>;
+    constexpr int EPI_WARPS = C::EPI_WARPS, STAGES = C::STAGES, OFF_STG = C::OFF_STG, OFF_BAR = C::OFF_BAR;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -164,7 +175,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // ------------------------------------------------------------ epilogue warps (this CTA's 128 rows)
         const int quad = warp & 3;
-        const int slice = warp >> 2;  // 64-column slice of the 256-column tile
+        const int slice = warp >> 2;  // column slice of the 256-column tile
+        constexpr int SLICE_COLS = C::SLICE_COLS;
         uint8_t* stg = smem + OFF_STG + warp * STG_BYTES;
         uint8_t* my_row = stg + lane * 128;
         const int sw = lane & 7;
@@ -177,8 +189,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
-            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * 64;
-            const int colb = n_blk * BN + slice * 64;
+            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * SLICE_COLS;
+            const int colb = n_blk * BN + slice * SLICE_COLS;
             // 32 accumulator columns -> bias / GELU / scale in fp32 (in place)
             auto load32 = [&](int c, float (&x)[32]) {
                 uint32_t v[32];
@@ -203,7 +215,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             };
             if (kOutF32) {
 #pragma unroll 1
-                for (int c = 0; c < 64; c += 32) {  // two 32-column fp32 staging tiles (128 B rows)
+                for (int c = 0; c < SLICE_COLS; c += 32) {  // 32-column fp32 staging tiles (128 B rows)
                     float x[32];
                     uint4 packed[8];
                     load32(c, x);
@@ -214,18 +226,21 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     flush(packed, colb + c);
                 }
             } else {
-                uint4 packed[8];  // one 64-column bf16 staging tile
+#pragma unroll 1
+                for (int c = 0; c < SLICE_COLS; c += 64) {  // 64-column bf16 staging tiles (128 B rows)
+                    uint4 packed[8];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float x[32];
-                    load32(32 * h, x);
+                    for (int h = 0; h < 2; ++h) {
+                        float x[32];
+                        load32(c + 32 * h, x);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        packed[4 * h + j] =
-                            make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                       pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                        for (int j = 0; j < 4; ++j)
+                            packed[4 * h + j] = make_uint4(
+                                pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                    }
+                    flush(packed, colb + c);
                 }
-                flush(packed, colb);
             }
             tc_fence_before();
             __syncwarp();
@@ -247,7 +262,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 template <bool kGelu, bool kOutF32>
 cudaError_t launch_variant2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
                             const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
-    auto kern = gemm2_bf16_tn_kernel<kGelu, kOutF32>;
+    constexpr int kEpiWarps = kGelu ? 16 : 8;
+    constexpr int SMEM_BYTES = Cfg<kEpiWarps>::SMEM_BYTES, THREADS = Cfg<kEpiWarps>::THREADS;
+    auto kern = gemm2_bf16_tn_kernel<kGelu, kOutF32, kEpiWarps>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
