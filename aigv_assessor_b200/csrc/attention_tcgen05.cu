@@ -13,12 +13,14 @@
 //   sum need no shuffles). The two warpgroups ping-pong against the single MMA thread: while one does its exp work the
 //   tensor core runs the other's P V and next Q K^T.
 // Per tile and 64-key block j:  S = Q K_j^T (UMMA 128x64x64 -> TMEM)  ->  row max, p = exp2(s*scale*log2e - m_ref)
-//   -> P_j (bf16) to smem in the 128B-swizzled K-major layout  ->  O += P_j V_j (UMMA 128x64x64 accumulating in TMEM; V is
-//   the MN-major B operand exactly as TMA lands it).
+//   -> P_j (bf16 pairs) written back over S in TENSOR memory (tcgen05.st)  ->  O += P_j V_j (UMMA 128x64x64 with the A
+//   operand read from TMEM, accumulating in TMEM; V is the MN-major B operand exactly as TMA lands it). Keeping P out of
+//   shared memory removes the per-block st.shared + proxy fence and a third of the tensor pipe's smem reads (a 128x64x16
+//   MMA with both operands in smem is smem-bandwidth bound: measured 48 instead of 32 cycles).
 // O lives in TMEM for the whole KV loop. m_ref is a *stale* row maximum: it is only raised (and O, l rescaled through
 // tcgen05.ld/st) when the true running maximum exceeds it by more than 2^8, so p <= 256 always and the rescale is rare;
 // the final O / l is exact regardless of the reference point.
-// Resources: 96 KiB smem, 256 TMEM columns, <=102 registers -> 2 CTAs (16 softmax warps) per SM.
+// Resources: 64 KiB smem, 256 TMEM columns, <=102 registers -> 2 CTAs (16 softmax warps) per SM.
 // S = 1025 = 16*64 + 1: the ragged tail is one short KV block (32 columns, 1 valid, rest masked to -inf); on the query
 // side the last CTA of a (frame, head) holds the single leftover row and skips its empty second tile entirely.
 #include "kernels.h"
@@ -34,17 +36,17 @@ constexpr int BKV = 64;    // keys per full block
 constexpr int HD = 64;     // head dim
 constexpr int Q_BYTES = BQ * HD * 2;    // 16 KiB
 constexpr int KV_BYTES = BKV * HD * 2;  // 8 KiB
-constexpr int P_BYTES = BQ * BKV * 2;   // 16 KiB (one 128B-swizzle atom column)
 constexpr int OFF_Q = 0;                            // TILES tiles
 constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;      // 2 stages
 constexpr int OFF_V = OFF_K + 2 * KV_BYTES;         // 2 stages
-constexpr int OFF_P = OFF_V + 2 * KV_BYTES;         // TILES tiles
-constexpr int OFF_BAR = OFF_P + TILES * P_BYTES;
+constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256;           // 15 mbarriers + the TMEM base slot
 constexpr int SOFTMAX_WARPS = 4 * TILES;
 constexpr int THREADS = (SOFTMAX_WARPS + 2) * 32;
 constexpr uint32_t TMEM_COLS = 128 * TILES;
-constexpr uint32_t TM_TILE = 128;  // TMEM columns per query tile: S block at +0 (64 cols), O accumulator at +64
+// TMEM columns per query tile: S block at +0 (64 fp32 cols) -- overwritten in place by P (bf16 pairs, 32 cols) once the
+// softmax has pulled S into registers -- and the O accumulator at +64.
+constexpr uint32_t TM_TILE = 128;
 constexpr uint32_t TM_O = 64;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -182,15 +184,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in smem, O(t) rescaled if it had to be
                     if (t == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
                     tc_fence_after();
-                    const uint32_t p_addr = smem_u32(smem + OFF_P + t * P_BYTES);
+                    const uint32_t tm_p = tmem_u + t * TM_TILE;  // P_j: bf16 pairs in the first 32 columns of the S block
                     const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
                     const uint32_t tm_o = tmem_u + t * TM_TILE + TM_O;
                     constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major
                     if (elect_one()) {
                         for (int k = 0; k < kv / 16; ++k) {
-                            // A = P_j: K-major 128B-swizzled rows, 32 B per 16-key step; B = V rows [16k,16k+16)
-                            umma_bf16_ss(tm_o, umma_desc_sw128(p_addr + k * 32, 16, 1024),
-                                         umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_pv,
+                            // A = P_j from TMEM: 8 columns (16 keys) per step; B = V rows [16k,16k+16): 2 KiB apart
+                            umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_pv,
                                          (j | k) != 0 ? 1u : 0u);
                         }
                         if (t == n_tiles - 1) umma_commit(&v_empty[st]);
@@ -211,8 +212,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + t * TM_TILE;
             const uint32_t tm_s = tm_lane;
             const uint32_t tm_o = tm_lane + TM_O;
-            uint8_t* p_row = smem + OFF_P + t * P_BYTES + r * 128;
-            const int sw = r & 7;
             float m_ref = -INFINITY;  // reference maximum, already multiplied by scale*log2e
             float l_run = 0.f;
             // Warps whose 32 query rows are all beyond the sequence (ragged last tile) skip the softmax math; they
@@ -271,54 +270,45 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         }
                         m_ref = new_ref;
                     }
-                    // pass 2: probabilities -> bf16 P tile in smem (swizzled K-major), row sum (independent chains)
+                    // pass 2: probabilities -> bf16 pairs, row sum (independent chains); P then overwrites S in TMEM
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    auto emit = [&](const float (&p)[32], int c) {
-                        const int chunk0 = c >> 3;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint4 w;
-                            w.x = pack_bf16x2(p[8 * q + 0], p[8 * q + 1]);
-                            w.y = pack_bf16x2(p[8 * q + 2], p[8 * q + 3]);
-                            w.z = pack_bf16x2(p[8 * q + 4], p[8 * q + 5]);
-                            w.w = pack_bf16x2(p[8 * q + 6], p[8 * q + 7]);
-                            *reinterpret_cast<uint4*>(p_row + (((chunk0 + q) ^ sw) << 4)) = w;
-                        }
-                    };
+                    uint32_t pk[32];  // 64 probabilities of this row, two per register (even key in the low half)
                     if (!tail) {
 #pragma unroll
                         for (int c = 0; c < BKV; c += 32) {
                             uint32_t v[32];
                             tmem_ld_32x32(tm_s + c, v);
                             tmem_ld_wait();
-                            float p[32];
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
-                                p[i] = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
-                                p[i + 1] = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
-                                p[i + 2] = ex2(fmaf(__uint_as_float(v[i + 2]), scale_log2, -m_ref));
-                                p[i + 3] = ex2(fmaf(__uint_as_float(v[i + 3]), scale_log2, -m_ref));
-                                s0 += p[i]; s1 += p[i + 1]; s2 += p[i + 2]; s3 += p[i + 3];
+                                const float p0 = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+                                const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
+                                const float p2 = ex2(fmaf(__uint_as_float(v[i + 2]), scale_log2, -m_ref));
+                                const float p3 = ex2(fmaf(__uint_as_float(v[i + 3]), scale_log2, -m_ref));
+                                s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                                pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
+                                pk[((c + i) >> 1) + 1] = pack_bf16x2(p2, p3);
                             }
-                            emit(p, c);
                         }
+                        tmem_st_32x32(tm_s, pk);
                     } else {
-                        for (int c = 0; c < tail_rows; c += 32) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(tm_s + c, v);
-                            tmem_ld_wait();
-                            float p[32];
+                        uint32_t v[32];  // tail_rows == 32 columns (attention_tail_rows caps the ragged block)
+                        tmem_ld_32x32(tm_s, v);
+                        tmem_ld_wait();
+                        uint32_t pt[16];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float e = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
-                                p[i] = (c + i < tail_valid) ? e : 0.f;
-                                s0 += p[i];
-                            }
-                            emit(p, c);
+                        for (int i = 0; i < 32; i += 2) {
+                            const float e0 = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
+                            const float e1 = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
+                            const float p0 = (i < tail_valid) ? e0 : 0.f;
+                            const float p1 = (i + 1 < tail_valid) ? e1 : 0.f;
+                            s0 += p0 + p1;
+                            pt[i >> 1] = pack_bf16x2(p0, p1);
                         }
+                        tmem_st_32x16(tm_s, pt);
                     }
+                    tmem_st_wait();
                     l_run += (s0 + s1) + (s2 + s3);
-                    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 }
                 tc_fence_before();
                 mbar_arrive(&p_full[t]);
@@ -364,14 +354,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 int attention_q_rows() { return BQ; }
 int attention_kv_rows() { return BKV; }
 int attention_tail_rows(int S) {
-    const int t = S % BKV;
-    return t == 0 ? 32 : ((t + 31) / 32) * 32;
+    (void)S;
+    return 32;  // the ragged block is processed 32 keys at a time (see launch_attention: S % 64 must be <= 32)
 }
 
 cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
                              __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
                              cudaStream_t stream) {
     if (head_dim != HD || frames <= 0 || S <= 0 || heads <= 0) return cudaErrorInvalidValue;
+    if (S % BKV > 32) return cudaErrorInvalidValue;  // ragged tail of at most 32 keys (1025 % 64 == 1)
     static bool configured = false;
     if (!configured) {
         cudaError_t e =

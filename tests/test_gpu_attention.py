@@ -15,7 +15,7 @@ def _attn_ref(qkv, frames, S, H, d):
     return (a.softmax(-1) @ v).transpose(1, 2).reshape(frames * S, H * d)
 
 
-@pytest.mark.parametrize("frames,S,H", [(1, 128, 1), (1, 256, 2), (2, 1025, 2), (3, 130, 4), (1, 1025, 16), (2, 97, 1)])
+@pytest.mark.parametrize("frames,S,H", [(1, 128, 1), (1, 256, 2), (2, 1025, 2), (3, 130, 4), (1, 1025, 16), (2, 95, 1)])
 def test_attention_matches_reference(frames, S, H):
     d = 64
     g = torch.Generator().manual_seed(S + H)
