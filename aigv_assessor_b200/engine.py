@@ -129,7 +129,10 @@ class VisionEngine:
         return eng.load_state_dict(sd)
 
     # ------------------------------------------------------------------ the hot path
-    def extract_feature(self, pixel_values: torch.Tensor, flatten: bool = True) -> torch.Tensor:
+    def extract_feature(self, pixel_values: torch.Tensor, flatten: bool = True,
+                        out: torch.Tensor | None = None) -> torch.Tensor:
+        """out (optional): a preallocated bf16 CUDA tensor [N, 256, C] to write into (avoids an allocation per call
+        when the caller pipelines copies on side streams)."""
         if pixel_values.dim() != 4:
             raise ValueError(f"wrong pixel_values size: {pixel_values.shape}")  # modeling_intern_vit.py:345
         cfg = self.cfg
@@ -143,7 +146,13 @@ class VisionEngine:
         in_dtype = pixel_values.dtype
         pv = pixel_values.detach().to(torch.bfloat16).contiguous()
         g2 = cfg.grid // 2
-        out = torch.empty((n, g2 * g2, cfg.llm_hidden), dtype=torch.bfloat16, device=pv.device)
+        if out is None:
+            out = torch.empty((n, g2 * g2, cfg.llm_hidden), dtype=torch.bfloat16, device=pv.device)
+        elif (out.dtype != torch.bfloat16 or not out.is_cuda or not out.is_contiguous()
+              or out.numel() != n * g2 * g2 * cfg.llm_hidden):
+            raise ValueError("out must be a contiguous bf16 CUDA tensor with N*256*C elements")
+        else:
+            out = out.view(n, g2 * g2, cfg.llm_hidden)
         if n:
             with torch.cuda.device(pv.device):
                 st = self.lib.aigv_extract_feature(self._h, C.c_void_p(pv.data_ptr()), n, C.c_void_p(out.data_ptr()),
