@@ -310,7 +310,9 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
     h->kpad = ((h->kreal + 63) / 64) * 64;
     h->W4 = 4 * h->D;
     h->T = (h->g / 2) * (h->g / 2);
-    if (h->hd != 64) return bad(AIGV_ERR_UNSUPPORTED, "attention kernel covers head_dim 64 only (InternViT-300M)");
+    if (h->hd != 64 && h->hd != 128)
+        return bad(AIGV_ERR_UNSUPPORTED, "attention kernel covers head_dim 64 (InternViT-300M) and 128 (InternViT-6B)");
+    if (h->S % 64 > 32) return bad(AIGV_ERR_UNSUPPORTED, "attention kernel needs (tokens mod 64) <= 32");
     if (h->g % 2) return bad(AIGV_ERR_UNSUPPORTED, "patch grid must be even for the 2x2 pixel shuffle");
     if (h->D % 32 || h->I % 32 || h->C % 32 || cfg->patch_size % 2)
         return bad(AIGV_ERR_UNSUPPORTED, "hidden/intermediate/llm widths must be multiples of 32");
@@ -780,7 +782,8 @@ int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias
 int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int heads, int head_dim, float scale,
                    void* stream) {
     if (!qkv_bf16 || !out_bf16 || frames <= 0 || S <= 0 || heads <= 0) return AIGV_ERR_INVALID;
-    if (head_dim != 64) return AIGV_ERR_UNSUPPORTED;
+    if (head_dim != 64 && head_dim != 128) return AIGV_ERR_UNSUPPORTED;
+    if (S % 64 > 32) return AIGV_ERR_UNSUPPORTED;
     const uint64_t M = (uint64_t)frames * S, D3 = 3ull * heads * head_dim;
     CUtensorMap tq, tk, tt;
     if (make_tmap_bf16_2d(&tq, qkv_bf16, M, D3, D3, attention_q_rows(), 64)) return AIGV_ERR_INVALID;

@@ -33,22 +33,31 @@ namespace {
 constexpr int BQ = 128;    // query rows per tile
 constexpr int TILES = 2;   // query tiles per CTA
 constexpr int BKV = 64;    // keys per full block
-constexpr int HD = 64;     // head dim
-constexpr int Q_BYTES = BQ * HD * 2;    // 16 KiB
-constexpr int KV_BYTES = BKV * HD * 2;  // 8 KiB
-constexpr int OFF_Q = 0;                            // TILES tiles
-constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;      // 2 stages
-constexpr int OFF_V = OFF_K + 2 * KV_BYTES;         // 2 stages
-constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;           // 15 mbarriers + the TMEM base slot
 constexpr int SOFTMAX_WARPS = 4 * TILES;
 constexpr int THREADS = (SOFTMAX_WARPS + 2) * 32;
-constexpr uint32_t TMEM_COLS = 128 * TILES;
-// TMEM columns per query tile: S block at +0 (64 fp32 cols) -- overwritten in place by P (bf16 pairs, 32 cols) once the
-// softmax has pulled S into registers -- and the O accumulator at +64.
-constexpr uint32_t TM_TILE = 128;
-constexpr uint32_t TM_O = 64;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+// Geometry per head dimension. Every operand tile is stored as 64-column (128-byte) swizzle atoms: HD/64 atoms side by
+// side for Q, K (K-major: the d axis is the MMA K dimension) and V (MN-major: the d axis is the MMA N dimension).
+template <int HD>
+struct Geo {
+    static constexpr int ATOMS = HD / 64;
+    static constexpr int Q_ATOM = BQ * 128;                 // bytes of one 64-column atom of a Q tile (16 KiB)
+    static constexpr int KV_ATOM = BKV * 128;               // bytes of one 64-column atom of a K / V tile (8 KiB)
+    static constexpr int Q_BYTES = ATOMS * Q_ATOM;
+    static constexpr int KV_BYTES = ATOMS * KV_ATOM;
+    static constexpr int OFF_Q = 0;                         // TILES tiles
+    static constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;   // 2 stages
+    static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;      // 2 stages
+    static constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;        // 15 mbarriers + the TMEM base slot
+    // TMEM columns per query tile: S block at +0 (64 fp32 cols) -- overwritten in place by P (bf16 pairs, 32 cols) once
+    // the softmax has pulled S into registers -- and the O accumulator (HD fp32 cols) at +64.
+    static constexpr uint32_t TM_O = 64;
+    static constexpr uint32_t TM_TILE = HD == 64 ? 128 : 256;
+    static constexpr uint32_t TMEM_COLS = TILES * TM_TILE;  // 256 (two CTAs per SM) or 512 (one)
+    static constexpr int MIN_CTAS = HD == 64 ? 2 : 1;
+};
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -56,10 +65,15 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(THREADS, 2)
+template <int HD>
+__global__ void __launch_bounds__(THREADS, Geo<HD>::MIN_CTAS)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_tail, __nv_bfloat16* __restrict__ out, int S, int D,
                      int tail_rows, float scale_log2) {
+    using G = Geo<HD>;
+    constexpr int ATOMS = G::ATOMS, Q_ATOM = G::Q_ATOM, KV_ATOM = G::KV_ATOM, Q_BYTES = G::Q_BYTES,
+                  KV_BYTES = G::KV_BYTES, OFF_Q = G::OFF_Q, OFF_K = G::OFF_K, OFF_V = G::OFF_V, OFF_BAR = G::OFF_BAR;
+    constexpr uint32_t TM_O = G::TM_O, TM_TILE = G::TM_TILE, TMEM_COLS = G::TMEM_COLS;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* q_full = bars + 0;
@@ -123,7 +137,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, n_tiles * Q_BYTES);
                 for (int t = 0; t < n_tiles; ++t)
-                    tma_load_2d(smem + OFF_Q + t * Q_BYTES, &tm_q, q_full, head * HD, row_base + q0 + t * BQ);
+                    for (int a = 0; a < ATOMS; ++a)
+                        tma_load_2d(smem + OFF_Q + t * Q_BYTES + a * Q_ATOM, &tm_q, q_full, head * HD + a * 64,
+                                    row_base + q0 + t * BQ);
             }
             __syncwarp();
             for (int j = 0; j < n_blocks; ++j) {
@@ -131,18 +147,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const uint32_t ph = (j >> 1) & 1;
                 const bool tail = j >= n_full;
                 const uint32_t bytes = tail ? tail_rows * HD * 2 : KV_BYTES;
+                const int atom_stride = tail ? tail_rows * 128 : KV_ATOM;  // the tail box is shorter, atoms pack tighter
                 const CUtensorMap* tm = tail ? &tm_tail : &tm_kv;
                 const int r = row_base + j * BKV;
                 mbar_wait(&k_empty[st], ph ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&k_full[st], bytes);
-                    tma_load_2d(smem + OFF_K + st * KV_BYTES, tm, &k_full[st], D + head * HD, r);
+                    for (int a = 0; a < ATOMS; ++a)
+                        tma_load_2d(smem + OFF_K + st * KV_BYTES + a * atom_stride, tm, &k_full[st],
+                                    D + head * HD + a * 64, r);
                 }
                 __syncwarp();
                 mbar_wait(&v_empty[st], ph ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&v_full[st], bytes);
-                    tma_load_2d(smem + OFF_V + st * KV_BYTES, tm, &v_full[st], 2 * D + head * HD, r);
+                    for (int a = 0; a < ATOMS; ++a)
+                        tma_load_2d(smem + OFF_V + st * KV_BYTES + a * atom_stride, tm, &v_full[st],
+                                    2 * D + head * HD + a * 64, r);
                 }
                 __syncwarp();
             }
@@ -162,13 +183,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 }
                 const uint32_t q_addr = smem_u32(smem + OFF_Q + t * Q_BYTES);
                 const uint32_t k_addr = smem_u32(smem + OFF_K + st * KV_BYTES);
+                const uint32_t k_atom = j >= n_full ? tail_rows * 128 : KV_ATOM;
                 const uint32_t idesc = umma_idesc_bf16(BQ, kv, 0, 0);
                 const uint32_t tm_s = tmem_u + t * TM_TILE;
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {
-                        umma_bf16_ss(tm_s, umma_desc_sw128(q_addr + k * 32, 16, 1024),
-                                     umma_desc_sw128(k_addr + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+                    for (int k = 0; k < HD / 16; ++k) {  // d axis: 4 steps of 32 B inside each 64-column atom
+                        umma_bf16_ss(tm_s, umma_desc_sw128(q_addr + (k >> 2) * Q_ATOM + (k & 3) * 32, 16, 1024),
+                                     umma_desc_sw128(k_addr + (k >> 2) * k_atom + (k & 3) * 32, 16, 1024), idesc,
+                                     k != 0 ? 1u : 0u);
                     }
                     umma_commit(&s_full[t]);
                     if (t == n_tiles - 1) umma_commit(&k_empty[st]);
@@ -187,11 +210,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     const uint32_t tm_p = tmem_u + t * TM_TILE;  // P_j: bf16 pairs in the first 32 columns of the S block
                     const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
                     const uint32_t tm_o = tmem_u + t * TM_TILE + TM_O;
-                    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major
+                    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
+                    const uint32_t v_lbo = j >= n_full ? tail_rows * 128 : KV_ATOM;  // stride between 64-column atoms
                     if (elect_one()) {
                         for (int k = 0; k < kv / 16; ++k) {
                             // A = P_j from TMEM: 8 columns (16 keys) per step; B = V rows [16k,16k+16): 2 KiB apart
-                            umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_sw128(v_addr + k * 2048, 16, 1024), idesc_pv,
+                            umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_sw128(v_addr + k * 2048, v_lbo, 1024), idesc_pv,
                                          (j | k) != 0 ? 1u : 0u);
                         }
                         if (t == n_tiles - 1) umma_commit(&v_empty[st]);
@@ -349,6 +373,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
 }
 
+template <int HD>
+cudaError_t launch_attention_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
+                                __nv_bfloat16* out, int frames, int S, int heads, float softmax_scale,
+                                cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Geo<HD>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((S + BQ * TILES - 1) / (BQ * TILES), heads, frames);
+    const float scale_log2 = softmax_scale * 1.4426950408889634f;
+    attention_fwd_kernel<HD><<<grid, THREADS, Geo<HD>::SMEM_BYTES, stream>>>(tm_q, tm_kv, tm_tail, out, S, heads * HD,
+                                                                             attention_tail_rows(S), scale_log2);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 int attention_q_rows() { return BQ; }
@@ -361,20 +403,11 @@ int attention_tail_rows(int S) {
 cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
                              __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
                              cudaStream_t stream) {
-    if (head_dim != HD || frames <= 0 || S <= 0 || heads <= 0) return cudaErrorInvalidValue;
+    if (frames <= 0 || S <= 0 || heads <= 0) return cudaErrorInvalidValue;
     if (S % BKV > 32) return cudaErrorInvalidValue;  // ragged tail of at most 32 keys (1025 % 64 == 1)
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    dim3 grid((S + BQ * TILES - 1) / (BQ * TILES), heads, frames);
-    const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    attention_fwd_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tm_q, tm_kv, tm_tail, out, S, heads * head_dim,
-                                                                attention_tail_rows(S), scale_log2);
-    return cudaGetLastError();
+    if (head_dim == 64) return launch_attention_hd<64>(tm_q, tm_kv, tm_tail, out, frames, S, heads, softmax_scale, stream);
+    if (head_dim == 128) return launch_attention_hd<128>(tm_q, tm_kv, tm_tail, out, frames, S, heads, softmax_scale, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace aigv

@@ -15,11 +15,12 @@ def _attn_ref(qkv, frames, S, H, d):
     return (a.softmax(-1) @ v).transpose(1, 2).reshape(frames * S, H * d)
 
 
-@pytest.mark.parametrize("frames,S,H", [(1, 128, 1), (1, 256, 2), (2, 1025, 2), (3, 130, 4), (1, 1025, 16), (2, 95, 1)])
-def test_attention_matches_reference(frames, S, H):
-    d = 64
-    g = torch.Generator().manual_seed(S + H)
-    qkv = (torch.randn((frames * S, 3 * H * d), generator=g) * 1.5).to(torch.bfloat16)
+@pytest.mark.parametrize("frames,S,H,d", [(1, 128, 1, 64), (1, 256, 2, 64), (2, 1025, 2, 64), (3, 130, 4, 64),
+                                          (1, 1025, 16, 64), (2, 95, 1, 64),
+                                          (1, 128, 1, 128), (2, 1025, 2, 128), (1, 1025, 25, 128), (2, 95, 3, 128)])
+def test_attention_matches_reference(frames, S, H, d):
+    g = torch.Generator().manual_seed(S + H + d)
+    qkv = (torch.randn((frames * S, 3 * H * d), generator=g) * (1.5 if d == 64 else 1.2)).to(torch.bfloat16)
     out = torch.full((frames * S, H * d), float("nan"), dtype=torch.bfloat16, device="cuda")
     lib = _lib.load()
     dq = dev(qkv)
@@ -65,8 +66,11 @@ def test_attention_monotone_scores_force_a_rescale_every_block():
     assert emax(out.float().cpu().numpy(), ref.cpu().numpy()) < 1e-2
 
 
-def test_attention_rejects_other_head_dims():
+def test_attention_rejects_what_it_does_not_cover():
     lib = _lib.load()
-    x = torch.zeros((128, 3 * 128), dtype=torch.bfloat16, device="cuda")
-    o = torch.zeros((128, 128), dtype=torch.bfloat16, device="cuda")
-    assert lib.aigv_attention(ptr(x), ptr(o), 1, 128, 1, 128, 0.1, stream()) == -5
+    x = torch.zeros((128, 3 * 96), dtype=torch.bfloat16, device="cuda")
+    o = torch.zeros((128, 96), dtype=torch.bfloat16, device="cuda")
+    assert lib.aigv_attention(ptr(x), ptr(o), 1, 128, 1, 96, 0.1, stream()) == -5   # head_dim 96
+    x = torch.zeros((100, 3 * 64), dtype=torch.bfloat16, device="cuda")
+    o = torch.zeros((100, 64), dtype=torch.bfloat16, device="cuda")
+    assert lib.aigv_attention(ptr(x), ptr(o), 1, 100, 1, 64, 0.1, stream()) == -5   # 100 % 64 = 36 > 32

@@ -39,6 +39,21 @@ def test_tiny_tower_vs_reference_golden(golden_dir, golden_meta):
     assert e_vit[1] < 1.5e-2 and e_out[0] < TOL
 
 
+def test_tiny_rms_qknorm_d128_tower_vs_reference_golden(golden_dir, golden_meta):
+    """InternViT-6B style blocks (RMSNorm, q/k RMSNorm over all heads, no qkv bias, layer scale 0.1, head_dim 128)."""
+    meta = golden_meta["tiny_rms"]
+    cfg = VisionPathConfig(**meta["cfg"])
+    assert cfg.head_dim == 128 and cfg.norm_type == "rms_norm" and cfg.qk_normalization
+    g = np.load(os.path.join(golden_dir, "tiny_rms.npz"))
+    eng = _engine(cfg, meta["w_seed"])
+    out = eng.extract_feature(_pv(1, cfg, meta["x_seed"])).float().cpu().numpy()
+    vit = eng.vit_hidden(1).cpu().numpy()
+    e_vit = vo.error_metrics(vit[:, ::41, ::16], g["vit_out_s"])
+    e_out = vo.error_metrics(out[:, ::8, ::16], g["out_s"])
+    print("tiny_rms: vit e_max/e_l2", e_vit, "out", e_out, "reference-bf16 e_max", meta["ref_bf16_e_max"])
+    assert e_vit[1] < 1.5e-2 and e_out[0] < TOL
+
+
 def test_vit300m_frame_vs_reference_golden(golden_dir, golden_meta):
     meta = golden_meta["vit300m"]
     cfg = VisionPathConfig(**meta["cfg"])
@@ -92,7 +107,7 @@ def test_shapes_dtypes_and_errors():
     with pytest.raises(ValueError):
         fresh.set_weight("mlp1.1.bias", np.zeros(3, np.float32))  # wrong shape
     with pytest.raises(ValueError):
-        VisionEngine(tiny(hidden_size=256, num_heads=2))  # head_dim 128 not covered yet
+        VisionEngine(tiny(hidden_size=192, num_heads=2))  # head_dim 96 is not covered
 
 
 def test_plugin_install_on_module_standin():
