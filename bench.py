@@ -266,6 +266,34 @@ def run_native(args, rank, local_rank, world):
         barrier()
         ms_e2e = f0.elapsed_time(f1)
 
+    # ---- HBM-bound kernels of the path: achieved GB/s against the measured copy bandwidth ---------------------------
+    bw = {}
+    if rank == 0:
+        fh, fw, nf = 720, 1280, frames
+        u8 = torch.randint(0, 256, (nf, fh, fw, 3), dtype=torch.uint8, device=dev)   # 177 MB > L2
+        for _ in range(2):
+            eng.preprocess_frames(u8, max_num=1)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(5):
+            eng.preprocess_frames(u8, max_num=1)
+        p1.record()
+        torch.cuda.synchronize()
+        pre_ms = p0.elapsed_time(p1) / 5
+        pre_bytes = nf * (fh * fw * 3 + 3 * cfg.image_size ** 2 * 2)
+        bw["preprocess_u8"] = {"GBps": pre_bytes / pre_ms / 1e6, "bytes_per_frame": pre_bytes / nf,
+                               "frames_per_s": nf / pre_ms * 1e3, "source": f"{fh}x{fw} uint8 -> 448x448 bf16 tile"}
+        del u8
+        M_rows = frames * cfg.tokens
+        if "norm" in prof:
+            b = M_rows * cfg.hidden_size * 6
+            bw["norm"] = {"GBps": b * prof["norm"][1] / prof["norm"][0] / 1e6, "bytes_per_launch": b}
+        if "pixel_shuffle_ln" in prof:
+            b = frames * cfg.num_patches * cfg.hidden_size * 4 + frames * cfg.out_tokens * cfg.shuffled_width * 2
+            bw["pixel_shuffle_ln"] = {"GBps": b * prof["pixel_shuffle_ln"][1] / prof["pixel_shuffle_ln"][0] / 1e6,
+                                      "bytes_per_launch": b}
+
     if world > 1:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,6 +345,7 @@ def run_native(args, rank, local_rank, world):
                          "flop_per_launch_avg": gemm_fl / max(gemm_launches, 1),
                          "whole_step_frac": value / world * cfg.flops_per_frame() / 1e12 / peaks["sustained"]},
             "kernels": kernels,
+            "bandwidth_kernels": {k: dict(v, frac_of_hbm_peak=v["GBps"] / peaks["hbm"]) for k, v in bw.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
             fps, secs = cpu_oracle_fps(cfg, sd, args.cpu_baseline_frames)
