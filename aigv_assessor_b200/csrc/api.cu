@@ -143,7 +143,7 @@ struct Profiler {
 
 struct PlanDev {
     int32_t *kx = nullptr, *bx = nullptr, *ky = nullptr, *by = nullptr;
-    int ksize_x = 0, ksize_y = 0, max_rows = 0;
+    int ksize_x = 0, ksize_y = 0, max_rows = 0, span_bytes = 0;
 };
 
 }  // namespace
@@ -708,6 +708,7 @@ static int get_plan(aigv_handle* h, int H, int W, int out_w, int out_h, PlanDev*
     p.ksize_x = plan_axis(W, out_w, kx, bx);
     p.ksize_y = plan_axis(H, out_h, ky, by);
     p.max_rows = plan_max_rows(by, out_h);
+    p.span_bytes = plan_max_span_bytes(bx, out_w);
     bool ok = dev_alloc(h, &p.kx, kx.size()) && dev_alloc(h, &p.bx, bx.size()) && dev_alloc(h, &p.ky, ky.size()) &&
               dev_alloc(h, &p.by, by.size());
     if (!ok) return -1;
@@ -734,13 +735,13 @@ int aigv_preprocess_u8(aigv_handle* h, const uint8_t* frames, int n, int H, int 
     PlanDev* p = nullptr;
     if (get_plan(h, H, W, tile * gi, tile * gj, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
     ResizePlan rp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile * gi, tile * gj};
-    AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, rp, p->max_rows, h->lut, tile, gi,
+    AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, rp, p->max_rows, p->span_bytes, h->lut, tile, gi,
                                     per_frame, 0, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
              "preprocess");
     if (with_thumb) {
         if (get_plan(h, H, W, tile, tile, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
         ResizePlan tp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile, tile};
-        AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, tp, p->max_rows, h->lut, tile, 1,
+        AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, tp, p->max_rows, p->span_bytes, h->lut, tile, 1,
                                         per_frame, blocks, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
                  "preprocess(thumbnail)");
     }

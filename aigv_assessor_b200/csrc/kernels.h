@@ -85,9 +85,10 @@ namespace aigv {
 // Host: Pillow precompute_coeffs + normalize_coeffs_8bpc for one axis; returns ksize.
 int plan_axis(int in_size, int out_size, std::vector<int32_t>& kk, std::vector<int32_t>& bounds);
 int plan_max_rows(const std::vector<int32_t>& by, int out_h);
+int plan_max_span_bytes(const std::vector<int32_t>& bx, int out_w);
 cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
-                                   int64_t row_stride, const ResizePlan& plan, int max_rows, const float* lut, int tile,
-                                   int tiles_x, int tiles_per_frame, int tile_offset, uint8_t* tiles_u8,
-                                   __nv_bfloat16* out, cudaStream_t stream);
+                                   int64_t row_stride, const ResizePlan& plan, int max_rows, int span_bytes,
+                                   const float* lut, int tile, int tiles_x, int tiles_per_frame, int tile_offset,
+                                   uint8_t* tiles_u8, __nv_bfloat16* out, cudaStream_t stream);
 
 }  // namespace aigv

@@ -29,20 +29,55 @@ __device__ __forceinline__ int clip8(int v) {
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
+// One block = a 32x32 block of output pixels of one frame.
+//   phase A: the source rows/columns this block's taps touch are copied into shared memory with coalesced 4-byte loads
+//   phase B: horizontal taps from shared memory -> uint8 rows in shared memory (Pillow's imTemp)
+//   phase C: vertical taps -> uint8 -> LUT -> bf16 NCHW (and optionally the uint8 HWC tile)
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W, int64_t frame_stride, int64_t row_stride,
                   ResizePlan plan, const float* __restrict__ lut, int tile, int tiles_x, int tiles_per_frame,
-                  int tile_offset, uint8_t* __restrict__ tiles_u8, __nv_bfloat16* __restrict__ out, int max_rows) {
-    extern __shared__ uint8_t tmp[];  // [max_rows][TX][3] horizontally resampled rows (uint8, as Pillow's imTemp)
+                  int tile_offset, uint8_t* __restrict__ tiles_u8, __nv_bfloat16* __restrict__ out, int max_rows,
+                  int span_bytes, int aligned4) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    uint8_t* srct = sm;                               // [max_rows][span_bytes] source window
+    uint8_t* tmp = sm + max_rows * span_bytes;        // [max_rows][TX][3] horizontally resampled rows
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int x_last = min(x0 + TX, plan.out_w) - 1;
     const int y_last = min(y0 + TY, plan.out_h) - 1;
     const int ysrc0 = plan.by[2 * y0];
-    const int ysrc1 = plan.by[2 * y_last] + plan.by[2 * y_last + 1];
-    const int nrows = ysrc1 - ysrc0;
+    const int nrows = plan.by[2 * y_last] + plan.by[2 * y_last + 1] - ysrc0;
+    const int xsrc0 = plan.bx[2 * x0];
+    const int xsrc1 = plan.bx[2 * x_last] + plan.bx[2 * x_last + 1];
     const uint8_t* src = frames + f * frame_stride;
+    const int byte0 = xsrc0 * 3;
+    const int byte1 = xsrc1 * 3;
 
-    // pass 1: horizontal taps for the source rows this block's vertical pass will touch
+    // phase A
+    if (aligned4) {
+        const int w0 = byte0 & ~3;                     // window starts at a 4-byte boundary of the row
+        const int nwords = (byte1 - w0 + 3) >> 2;
+        const int row_words = static_cast<int>(row_stride >> 2);
+        for (int idx = threadIdx.x; idx < nrows * nwords; idx += blockDim.x) {
+            const int rr = idx / nwords, ww = idx - rr * nwords;
+            const int word = (w0 >> 2) + ww;
+            uint32_t v = 0;
+            if (word < row_words)                      // never read past the end of the row
+                v = __ldg(reinterpret_cast<const uint32_t*>(src + static_cast<int64_t>(ysrc0 + rr) * row_stride) + word);
+            *reinterpret_cast<uint32_t*>(srct + rr * span_bytes + ww * 4) = v;
+        }
+    } else {
+        const int w0 = byte0;
+        const int nbytes = byte1 - w0;
+        for (int idx = threadIdx.x; idx < nrows * nbytes; idx += blockDim.x) {
+            const int rr = idx / nbytes, bb = idx - rr * nbytes;
+            srct[rr * span_bytes + bb] = src[static_cast<int64_t>(ysrc0 + rr) * row_stride + w0 + bb];
+        }
+    }
+    const int win0 = aligned4 ? (byte0 & ~3) : byte0;  // byte offset (within the row) of srct column 0
+    __syncthreads();
+
+    // phase B: horizontal taps
     for (int idx = threadIdx.x; idx < nrows * TX; idx += blockDim.x) {
         const int rr = idx / TX, xx = idx % TX;
         const int X = x0 + xx;
@@ -50,7 +85,7 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W, int64_t fram
         if (X < plan.out_w) {
             const int xmin = plan.bx[2 * X], cnt = plan.bx[2 * X + 1];
             const int32_t* k = plan.kx + static_cast<size_t>(X) * plan.ksize_x;
-            const uint8_t* p = src + static_cast<int64_t>(ysrc0 + rr) * row_stride + xmin * 3;
+            const uint8_t* p = srct + rr * span_bytes + (xmin * 3 - win0);
             for (int t = 0; t < cnt; ++t) {
                 const int kk = __ldg(k + t);
                 a0 += p[3 * t + 0] * kk;
@@ -65,7 +100,7 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W, int64_t fram
     }
     __syncthreads();
 
-    // pass 2: vertical taps, normalise, write bf16 NCHW (and optionally the uint8 HWC tile)
+    // phase C: vertical taps, normalise, write bf16 NCHW (and optionally the uint8 HWC tile)
     const int tx = threadIdx.x % TX;
     const int X = x0 + tx;
     if (X >= plan.out_w) return;
@@ -164,12 +199,27 @@ int plan_max_rows(const std::vector<int32_t>& by, int out_h) {
     return best;
 }
 
+// Widest source window (in bytes, rounded for 4-byte staging) any 32-column output block touches.
+int plan_max_span_bytes(const std::vector<int32_t>& bx, int out_w) {
+    int best = 4;
+    for (int x0 = 0; x0 < out_w; x0 += TX) {
+        const int xl = (x0 + TX < out_w ? x0 + TX : out_w) - 1;
+        const int b0 = (bx[2 * x0] * 3) & ~3;
+        const int b1 = (bx[2 * xl] + bx[2 * xl + 1]) * 3;
+        const int n = ((b1 - b0 + 3) >> 2) << 2;
+        if (n > best) best = n;
+    }
+    return best + 4;
+}
+
 cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
-                                   int64_t row_stride, const ResizePlan& plan, int max_rows, const float* lut, int tile,
-                                   int tiles_x, int tiles_per_frame, int tile_offset, uint8_t* tiles_u8,
-                                   __nv_bfloat16* out, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(max_rows) * TX * 3;
+                                   int64_t row_stride, const ResizePlan& plan, int max_rows, int span_bytes,
+                                   const float* lut, int tile, int tiles_x, int tiles_per_frame, int tile_offset,
+                                   uint8_t* tiles_u8, __nv_bfloat16* out, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(max_rows) * (TX * 3 + span_bytes);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    const int aligned4 = ((reinterpret_cast<uintptr_t>(frames) | static_cast<uintptr_t>(frame_stride) |
+                           static_cast<uintptr_t>(row_stride)) & 3) == 0;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
@@ -177,7 +227,8 @@ cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, i
     }
     dim3 grid((plan.out_w + TX - 1) / TX, (plan.out_h + TY - 1) / TY, n);
     preprocess_kernel<<<grid, 256, smem, stream>>>(frames, H, W, frame_stride, row_stride, plan, lut, tile, tiles_x,
-                                                   tiles_per_frame, tile_offset, tiles_u8, out, max_rows);
+                                                   tiles_per_frame, tile_offset, tiles_u8, out, max_rows, span_bytes,
+                                                   aligned4);
     return cudaGetLastError();
 }
 

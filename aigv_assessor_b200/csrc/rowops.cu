@@ -260,6 +260,63 @@ pixel_shuffle_ln_kernel(const float* __restrict__ x, const float* __restrict__ w
     }
 }
 
+// Register-resident variant for D = 128 * VPL: the 4 x D gathered row is read from global memory exactly once.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+pixel_shuffle_ln_reg_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                            __nv_bfloat16* __restrict__ y, int n, int g, float eps) {
+    constexpr int D = 128 * VPL;
+    const int g2 = g >> 1;
+    const int orow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (orow >= n * g2 * g2) return;
+    const int f = orow / (g2 * g2);
+    const int ij = orow % (g2 * g2);
+    const int I = ij / g2, J = ij % g2;
+    const float* frame = x + static_cast<size_t>(f) * (g * g + 1) * D;
+    float4 v[4][VPL];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const float4* xs = reinterpret_cast<const float4*>(
+            frame + static_cast<size_t>(1 + g * (2 * I + (s >> 1)) + (2 * J + (s & 1))) * D);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) v[s][i] = xs[(i >> 1) * 64 + 2 * lane + (i & 1)];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) sum += (v[s][i].x + v[s][i].y) + (v[s][i].z + v[s][i].w);
+    const float mean = warp_sum(sum) * (1.0f / (4 * D));
+    float q = 0.f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float a0 = v[s][i].x - mean, a1 = v[s][i].y - mean, a2 = v[s][i].z - mean, a3 = v[s][i].w - mean;
+            q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / (4 * D)) + eps);
+    __nv_bfloat16* yr = y + static_cast<size_t>(orow) * 4 * D;
+    auto nrm = [&](float xv, float wv, float bv) { return (xv - mean) * rstd * wv + bv; };
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int i = 0; i < VPL; i += 2) {
+            const int col = s * D + ((i >> 1) * 64 + 2 * lane) * 4;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + col));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + col + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + col));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(b + col + 4));
+            uint4 o;
+            o.x = pack_bf16x2(nrm(v[s][i].x, w0.x, b0.x), nrm(v[s][i].y, w0.y, b0.y));
+            o.y = pack_bf16x2(nrm(v[s][i].z, w0.z, b0.z), nrm(v[s][i].w, w0.w, b0.w));
+            o.z = pack_bf16x2(nrm(v[s][i + 1].x, w1.x, b1.x), nrm(v[s][i + 1].y, w1.y, b1.y));
+            o.w = pack_bf16x2(nrm(v[s][i + 1].z, w1.z, b1.z), nrm(v[s][i + 1].w, w1.w, b1.w));
+            *reinterpret_cast<uint4*>(yr + col) = o;
+        }
+}
+
 inline int grid_for(size_t work_items, int threads, int cap = 148 * 16) {
     size_t b = (work_items + threads - 1) / threads;
     if (b > static_cast<size_t>(cap)) b = cap;
@@ -310,7 +367,12 @@ cudaError_t launch_pixel_shuffle_ln(const float* x, const float* w, const float*
                                     int D, float eps, int apply_ln, cudaStream_t stream) {
     if (n <= 0 || (g % 2) != 0 || (D % 8) != 0) return cudaErrorInvalidValue;
     const int rows = n * (g / 2) * (g / 2);
-    pixel_shuffle_ln_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, w, b, y, n, g, D, eps, apply_ln);
+    if (apply_ln && D == 1024)
+        pixel_shuffle_ln_reg_kernel<8><<<(rows + 7) / 8, 256, 0, stream>>>(x, w, b, y, n, g, eps);
+    else if (apply_ln && D == 256)
+        pixel_shuffle_ln_reg_kernel<2><<<(rows + 7) / 8, 256, 0, stream>>>(x, w, b, y, n, g, eps);
+    else
+        pixel_shuffle_ln_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, w, b, y, n, g, D, eps, apply_ln);
     return cudaGetLastError();
 }
 

@@ -111,7 +111,7 @@ def cpu_oracle_fps(cfg, sd, frames, repeats=1):
     return frames / best, best
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """CPU arm: the oracle port of the reference's path, all host threads, bounded sample per step."""
     if rank != 0:
         return
@@ -144,10 +144,10 @@ def run_reference(args, rank, world):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
-def run_native(args, rank, local_rank, world):
+def run_native(args, rank, local_rank, world, out):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -352,10 +352,30 @@ def run_native(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"{args.cpu_baseline_frames} frame(s) of the same workload through the torch-CPU "
                                               f"fp32 oracle port ({secs:.1f} s, {os.cpu_count()} threads)"}
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class OnlyJsonOnStdout:
+    """Libraries (NCCL's version banner, torchrun warnings) write to fd 1; the driver wants exactly ONE JSON line there.
+    Everything written to stdout while this is active goes to stderr; emit() writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        os.write(self._real, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._real, 1)
+        os.close(self._real)
+        return False
 
 
 def main():
@@ -374,10 +394,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_native(args, rank, local_rank, world)
+    with OnlyJsonOnStdout() as out:
+        if args.impl == "reference":
+            run_reference(args, rank, world, out)
+        else:
+            run_native(args, rank, local_rank, world, out)
 
 
 if __name__ == "__main__":

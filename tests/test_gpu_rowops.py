@@ -73,9 +73,9 @@ def test_im2col_and_assemble_equal_oracle_embeddings():
     assert emax(x.cpu().numpy(), ref) < 1e-5
 
 
-@pytest.mark.parametrize("apply_ln", [0, 1])
-def test_pixel_shuffle_ln(apply_ln):
-    n, g, D = 2, 32, 128
+@pytest.mark.parametrize("apply_ln,D", [(0, 128), (1, 128), (1, 256), (1, 1024)])
+def test_pixel_shuffle_ln(apply_ln, D):
+    n, g = 2, 32
     rng = np.random.default_rng(8)
     x = synth.bf16_round(rng.standard_normal((n, g * g + 1, D)).astype(np.float32))
     w = (1 + 0.1 * rng.standard_normal(4 * D)).astype(np.float32)
