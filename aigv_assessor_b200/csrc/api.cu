@@ -53,19 +53,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int f32, uint64_t rows, uin
     return r == CUDA_SUCCESS ? 0 : -3;
 }
 
-// Which GEMM kernel the path uses: the CTA-pair kernel (default) or the single-CTA one (AIGV_GEMM=1cta, bring-up aid).
-static bool gemm_use_pair() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("AIGV_GEMM");
-        v = (e && strcmp(e, "1cta") == 0) ? 0 : 1;
-    }
-    return v == 1;
-}
-static int w_box_rows() { return gemm_use_pair() ? gemm2_box_rows_b() : gemm_box_rows_b(); }
+static int w_box_rows() { return gemm_box_rows_b(); }
 static cudaError_t run_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
                             const GemmEpilogue& ep, int num_sms, cudaStream_t st) {
-    return gemm_use_pair() ? launch_gemm2(a, b, c, M, N, K, ep, num_sms, st) : launch_gemm(a, b, c, M, N, K, ep, num_sms, st);
+    return launch_gemm(a, b, c, M, N, K, ep, num_sms, st);
 }
 
 static int device_num_sms() {

@@ -1,4 +1,4 @@
-// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogue.
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogue, CTA-pair (cta_group::2) form.
 //
 //   C[M,N] (op)= colscale * act( A[M,K] (bf16, K contiguous) x W[N,K]^T (bf16, nn.Linear weight layout) + bias )
 //   op is a TMA store (bf16 or fp32) or a TMA reduce-add into the fp32 residual stream (x += ...); fp32 math.
@@ -8,10 +8,17 @@
 //   mlp.fc1 + GELU (:189,193-194)                mlp.fc2 + *ls2 + residual (:190,195,226)
 //   patch_embedding conv as im2col GEMM (:97)    mlp1[1]+GELU, mlp1[3] (modeling_internvl_chat.py eval2:240-242)
 //
-// Tile 128x256x64, 4-stage TMA->smem ring (128B swizzle), UMMA M=128 N=256 K=16 issued by one thread,
-// two 256-column fp32 accumulators in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Warps 0-7: epilogue (warp%4 = TMEM lane quadrant, warp/4 = column half; results are staged through a 128B-swizzled
-// smem tile per warp and leave by TMA store / reduce-add); warp 8: TMA producer; warp 9: MMA issuer.
+// A CTA pair (cluster of 2, one TPC) owns a 256x256 output tile; UMMA M=256 N=256 K=16 is issued by the leader CTA and
+// each CTA stages only its own 128 rows of A and its own 128 rows of W (half of N) per k-block: 32 KiB instead of 48 KiB
+// of TMA fill + operand reads per 128x256x64 of MACs. A single-CTA 128x256 tile is shared-memory-bandwidth bound (~96
+// B/clk of operand reads + ~94 B/clk of TMA fills against ~128 B/clk; measured 54-73% tensor-pipe active); the pair
+// needs ~125 B/clk at full MMA rate and measures 90% tensor-pipe active on the K >= 1024 shapes.
+// Results are staged through a 128B-swizzled smem tile per epilogue warp and leave by TMA store / reduce-add.
+//   warp 8: TMA producer (each CTA loads its own operands; transaction bytes are credited to the LEADER's full barrier)
+//   warp 9: leader only: MMA issuer; commits are multicast to both CTAs' empty / accumulator-full barriers
+//   warps 0-15: epilogue of this CTA's 128 rows (warp%4 = TMEM lane quadrant, warp/4 = 64-column slice; 4 warps per
+//   SMSP hide the GELU / TMEM-load latencies); they release the accumulator stage on the leader's barrier (remote arrive)
+//   warp 16: TMA producer, warp 17: MMA issuer
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -19,19 +26,30 @@ namespace aigv {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int BM = 128;          // rows per CTA (256 per pair)
+constexpr int BN = 256;          // columns per pair tile
+constexpr int BNH = 128;         // W rows staged per CTA
+constexpr int BK = 64, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_BYTES = BNH * BK * 2;  // 16 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = (EPI_WARPS + 2) * 32;
-constexpr int STG_BYTES = 4096;  // per epilogue warp: 32 rows x 128 B (64 bf16 or 32 fp32 columns), 128B-swizzled
-constexpr int OFF_STG = STAGES * STAGE_BYTES;
-constexpr int OFF_BAR = OFF_STG + EPI_WARPS * STG_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr int STG_BYTES = 4096;
 constexpr uint32_t TMEM_COLS = 512;
 
-// acc + bias -> act -> * colscale, on 32 consecutive columns starting at col0 (fp32 registers).
+// Two shapes of the same kernel: the GELU epilogue is instruction-issue heavy and wants 16 epilogue warps (4 per SMSP)
+// at the price of one pipeline stage; the plain / residual epilogues are lighter and keep 8 warps and 6 stages.
+template <int kEpiWarps>
+struct Cfg {
+    static constexpr int EPI_WARPS = kEpiWarps;          // multiple of 4: warp%4 = TMEM lane quadrant
+    static constexpr int SLICES = kEpiWarps / 4;         // column slices of the 256-column tile
+    static constexpr int SLICE_COLS = BN / SLICES;       // 64 or 128 columns per warp
+    static constexpr int STAGES = kEpiWarps == 16 ? 5 : 6;
+    static constexpr int THREADS = (kEpiWarps + 2) * 32;
+    static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_STG + kEpiWarps * STG_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+};
+
 template <bool kGelu>
 __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep) {
     if (ep.bias) {
@@ -54,10 +72,12 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
     }
 }
 
-template <bool kGelu, bool kOutF32>
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool kGelu, bool kOutF32, int kEpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<kEpiWarps>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpilogue ep) {
+                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpilogue ep) {
+    using C = Cfg<kEpiWarps>;
+    constexpr int EPI_WARPS = C::EPI_WARPS, STAGES = C::STAGES, OFF_STG = C::OFF_STG, OFF_BAR = C::OFF_BAR;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -67,7 +87,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_m = (M + BM - 1) / BM;
+    const uint32_t rank = cluster_ctarank();   // 0 = leader
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
     const int num_n = (N + BN - 1) / BN;
     const int num_k = (K + BK - 1) / BK;
     const int num_tiles = num_m * num_n;
@@ -76,137 +99,117 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         printf("aigv gemm: dynamic smem base not 1024B aligned\n");
         __trap();
     }
-    if (warp == 8 && lane == 0) {
+    if (warp == EPI_WARPS && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
     }
-    if (warp == 9) {
+    if (warp == EPI_WARPS + 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(&full_bar[s], 1);
-                mbar_init(&empty_bar[s], 1);
+                mbar_init(&full_bar[s], 1);    // leader: its own producer's arrive.expect_tx (bytes of BOTH CTAs)
+                mbar_init(&empty_bar[s], 1);   // multicast commit from the leader's MMA thread
             }
             for (int s = 0; s < 2; ++s) {
-                mbar_init(&tfull_bar[s], 1);
-                mbar_init(&tempty_bar[s], EPI_WARPS);
+                mbar_init(&tfull_bar[s], 1);                // multicast commit
+                mbar_init(&tempty_bar[s], 2 * EPI_WARPS);   // leader: epilogue warps of both CTAs
             }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc<TMEM_COLS>(tmem_slot);
-        tmem_relinquish();
+        tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+        tmem_relinquish_pair();
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / TMA credit / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
-        // ------------------------------------------------------------ TMA producer
-        // (whole warp converged, one elected lane issues: keeps addresses/coordinates in uniform registers)
+    if (warp == EPI_WARPS) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const int row_a = m_blk * 2 * BM + rank * BM;
+            const int row_b = n_blk * BN + rank * BNH;
             for (int kb = 0; kb < num_k; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);
+                    tma_load_2d_pair(sa + A_BYTES, &tmB, &full_bar[stage], kb * BK, row_b);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 9) {
-        // ------------------------------------------------------------ MMA issuer
-        // The warp runs the loop converged and one elected lane issues the tcgen05 instructions; inside a divergent
-        // `if (lane == 0)` every UTCHMMA gets wrapped in an ELECT/BRA.U.ANY loop with R2UR transfers.
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        int stage = 0;
-        uint32_t phase = 0;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_u + acc * BN;
-            for (int kb = 0; kb < num_k; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+    } else if (warp == EPI_WARPS + 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + A_BYTES;
-                if (elect_one()) {
+                const uint32_t tmem_d = tmem_u + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-                        const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-                        umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+                            const uint64_t db = umma_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                            umma_bf16_ss_pair(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_pair(&empty_bar[stage], 3);                           // free the slot in both CTAs
+                        if (kb == num_k - 1) umma_commit_pair(&tfull_bar[acc], 3);        // accumulator -> both epilogues
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                    if (kb == num_k - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
     } else {
-        // ------------------------------------------------------------ epilogue warps
-        // TMEM -> registers (tcgen05.ld, lane == row) -> fp32 math -> 128B-swizzled smem staging tile -> TMA store
-        // (or TMA reduce-add into the fp32 residual stream): global traffic is fully coalesced and asynchronous.
+        // ------------------------------------------------------------ epilogue warps (this CTA's 128 rows)
         const int quad = warp & 3;
-        const int half = warp >> 2;
+        const int slice = warp >> 2;  // column slice of the 256-column tile
+        constexpr int SLICE_COLS = C::SLICE_COLS;
         uint8_t* stg = smem + OFF_STG + warp * STG_BYTES;
         uint8_t* my_row = stg + lane * 128;
         const int sw = lane & 7;
+        const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+        const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row0 = m_blk * BM + quad * 32;
-            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * 128;
-            constexpr int CHUNK = kOutF32 ? 32 : 64;  // columns per staged tile (128 B per row)
-#pragma unroll 1
-            for (int c = 0; c < 128; c += CHUNK) {
-                const int col0 = n_blk * BN + half * 128 + c;
+            const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
+            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * SLICE_COLS;
+            const int colb = n_blk * BN + slice * SLICE_COLS;
+            // 32 accumulator columns -> bias / GELU / scale in fp32 (in place)
+            auto load32 = [&](int c, float (&x)[32]) {
                 uint32_t v[32];
-                float x[32];
-                uint4 packed[8];
                 tmem_ld_32x32(tm + c, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                if (col0 < N) epilogue_math<kGelu>(x, col0, ep);
-                if (kOutF32) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        packed[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
-                                               __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        packed[j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                               pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
-                    tmem_ld_32x32(tm + c + 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                    if (col0 + 32 < N) epilogue_math<kGelu>(x, col0 + 32, ep);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        packed[4 + j] = make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                                   pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
-                }
-                // the previous TMA store of this warp must have finished reading the staging tile
-                if (lane == 0) tma_store_wait_read<0>();
+                if (colb + c < N) epilogue_math<kGelu>(x, colb + c, ep);
+            };
+            auto flush = [&](const uint4 (&packed)[8], int col0) {
+                if (lane == 0) tma_store_wait_read<0>();  // previous TMA store has finished reading the staging tile
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = packed[j];
@@ -217,10 +220,39 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     else tma_store_2d(&tmC, stg, col0, row0);
                     tma_store_commit();
                 }
+            };
+            if (kOutF32) {
+#pragma unroll 1
+                for (int c = 0; c < SLICE_COLS; c += 32) {  // 32-column fp32 staging tiles (128 B rows)
+                    float x[32];
+                    uint4 packed[8];
+                    load32(c, x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        packed[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                                               __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+                    flush(packed, colb + c);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < SLICE_COLS; c += 64) {  // 64-column bf16 staging tiles (128 B rows)
+                    uint4 packed[8];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float x[32];
+                        load32(c + 32 * h, x);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            packed[4 * h + j] = make_uint4(
+                                pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+                    }
+                    flush(packed, colb + c);
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -228,40 +260,42 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 9) {
+    cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer can still touch its smem / barriers / TMEM
+    if (warp == EPI_WARPS + 1) {
         tc_fence_after();
-        tmem_dealloc<TMEM_COLS>(tmem_base);
+        tmem_dealloc_pair<TMEM_COLS>(tmem_base);
     }
 }
 
 template <bool kGelu, bool kOutF32>
 cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
-                           const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
-    auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32>;
+                            const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+    constexpr int kEpiWarps = kGelu ? 16 : 8;
+    constexpr int SMEM_BYTES = Cfg<kEpiWarps>::SMEM_BYTES, THREADS = Cfg<kEpiWarps>::THREADS;
+    auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32, kEpiWarps>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, ep);
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    int pairs = num_sms / 2;
+    if (tiles < pairs) pairs = tiles;
+    kern<<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, ep);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int gemm_box_rows_a() { return BM; }
-int gemm_box_rows_b() { return BN; }
+int gemm_box_rows_b() { return BNH; }
 int gemm_box_cols() { return BK; }
-
 int gemm_box_rows_c() { return 32; }
 int gemm_box_cols_c(bool out_f32) { return out_f32 ? 32 : 64; }
 
 cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
-                        const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+                         const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
     if (ep.accumulate && !ep.out_f32) return cudaErrorInvalidValue;
     if (ep.gelu) {

@@ -26,21 +26,15 @@ inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, 
     return make_tmap_2d(out, base, 0, rows, cols, ld, box_rows, box_cols);
 }
 
-// ---- GEMM ------------------------------------------------------------------------------------------------------
+// ---- GEMM (CTA-pair kernel, gemm_tcgen05.cu) ---------------------------------------------------------------------
+// A box = [gemm_box_rows_a(), 64], W box = [gemm_box_rows_b(), 64], C box = [gemm_box_rows_c(), gemm_box_cols_c(f32)].
 int gemm_box_rows_a();
 int gemm_box_rows_b();
 int gemm_box_cols();
 int gemm_box_rows_c();
 int gemm_box_cols_c(bool out_f32);
-// tmC: output map with box [gemm_box_rows_c(), gemm_box_cols_c(out_f32)].
 cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
                         const GemmEpilogue& ep, int num_sms, cudaStream_t stream);
-
-// 2-CTA (cta_group::2) variant: 256x256 tile per CTA pair; A box rows = gemm2_box_rows_a(), W box rows = gemm2_box_rows_b().
-int gemm2_box_rows_a();
-int gemm2_box_rows_b();
-cudaError_t launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
-                         const GemmEpilogue& ep, int num_sms, cudaStream_t stream);
 
 // ---- attention -------------------------------------------------------------------------------------------------
 // qkv: bf16 [frames*S, 3*D] with channel order (three, head, d); out: bf16 [frames*S, D] (head-major channels).

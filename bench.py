@@ -337,7 +337,7 @@ def run_native(args, rank, local_rank, world, out):
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": host[0].numel() * 2,
                     "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm2_bf16_tn_kernel (tcgen05 cta_group::2, all GEMM launches of the timed steps)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05 cta_group::2, all GEMM launches of the timed steps)",
                          "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["sustained"]) if achieved else None, "traffic": traffic,
                          "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; burst {peaks['burst']})",
