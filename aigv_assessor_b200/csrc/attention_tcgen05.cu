@@ -298,6 +298,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                     uint32_t pk[32];  // 64 probabilities of this row, two per register (even key in the low half)
                     if (!tail) {
+                        // packed fp32x2 arithmetic (FFMA2 / FADD2): one issue slot per two keys for the scale and the sum
+                        const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_ref, -m_ref);
+                        f32x2 sum01 = pack2(0.f, 0.f), sum23 = pack2(0.f, 0.f);
 #pragma unroll
                         for (int c = 0; c < BKV; c += 32) {
                             uint32_t v[32];
@@ -305,15 +308,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
-                                const float p0 = ex2(fmaf(__uint_as_float(v[i]), scale_log2, -m_ref));
-                                const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_ref));
-                                const float p2 = ex2(fmaf(__uint_as_float(v[i + 2]), scale_log2, -m_ref));
-                                const float p3 = ex2(fmaf(__uint_as_float(v[i + 3]), scale_log2, -m_ref));
-                                s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+                                float x0, x1, x2, x3;
+                                unpack2(fma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2), x0, x1);
+                                unpack2(fma2(pack2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), sc2, nm2), x2, x3);
+                                const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
+                                sum01 = add2(sum01, pack2(p0, p1));
+                                sum23 = add2(sum23, pack2(p2, p3));
                                 pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
                                 pk[((c + i) >> 1) + 1] = pack_bf16x2(p2, p3);
                             }
                         }
+                        unpack2(sum01, s0, s1);
+                        unpack2(sum23, s2, s3);
                         tmem_st_32x32(tm_s, pk);
                     } else {
                         uint32_t v[32];  // tail_rows == 32 columns (attention_tail_rows caps the ragged block)
