@@ -46,11 +46,12 @@ struct Geo {
     static constexpr int KV_ATOM = BKV * 128;               // bytes of one 64-column atom of a K / V tile (8 KiB)
     static constexpr int Q_BYTES = ATOMS * Q_ATOM;
     static constexpr int KV_BYTES = ATOMS * KV_ATOM;
+    static constexpr int STAGES = HD == 64 ? 4 : 2;         // K/V ring depth (TMA latency ~ two block times)
     static constexpr int OFF_Q = 0;                         // TILES tiles
-    static constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;   // 2 stages
-    static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;      // 2 stages
-    static constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256;        // 15 mbarriers + the TMEM base slot
+    static constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;   // STAGES stages
+    static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES; // STAGES stages
+    static constexpr int OFF_BAR = OFF_V + STAGES * KV_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;        // 1 + 4*STAGES + 3*TILES mbarriers + the TMEM base slot
     // TMEM columns per query tile: S block at +0 (64 fp32 cols) -- overwritten in place by P (bf16 pairs, 32 cols) once
     // the softmax has pulled S into registers -- and the O accumulator (HD fp32 cols) at +64.
     static constexpr uint32_t TM_O = 64;
@@ -74,17 +75,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     constexpr int ATOMS = G::ATOMS, Q_ATOM = G::Q_ATOM, KV_ATOM = G::KV_ATOM, Q_BYTES = G::Q_BYTES,
                   KV_BYTES = G::KV_BYTES, OFF_Q = G::OFF_Q, OFF_K = G::OFF_K, OFF_V = G::OFF_V, OFF_BAR = G::OFF_BAR;
     constexpr uint32_t TM_O = G::TM_O, TM_TILE = G::TM_TILE, TMEM_COLS = G::TMEM_COLS;
+    constexpr int STAGES = G::STAGES;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;    // [2]
-    uint64_t* k_empty = bars + 3;   // [2]
-    uint64_t* v_full = bars + 5;    // [2]
-    uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;    // [TILES] S_j in TMEM (also: every earlier MMA, incl. this tile's P_{j-1} V_{j-1}, done)
-    uint64_t* p_full = bars + 11;   // [TILES] S_j consumed, P_j written to smem, O rescaled if needed
-    uint64_t* o_done = bars + 13;   // [TILES] last P V accumulated
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* k_full = q_full + 1;           // [STAGES]
+    uint64_t* k_empty = k_full + STAGES;     // [STAGES]
+    uint64_t* v_full = k_empty + STAGES;     // [STAGES]
+    uint64_t* v_empty = v_full + STAGES;     // [STAGES]
+    uint64_t* s_full = v_empty + STAGES;     // [TILES] S_j in TMEM (also: every earlier MMA, incl. this tile's P V, done)
+    uint64_t* p_full = s_full + TILES;       // [TILES] S_j consumed, P_j written to TMEM, O rescaled if needed (1 arrival/warp)
+    uint64_t* o_done = p_full + TILES;       // [TILES] last P V accumulated
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + TILES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -109,7 +111,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (warp == SOFTMAX_WARPS + 1) {
         if (lane == 0) {
             mbar_init(q_full, 1);
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&k_full[s], 1);
                 mbar_init(&k_empty[s], 1);
                 mbar_init(&v_full[s], 1);
@@ -117,7 +119,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
             for (int t = 0; t < TILES; ++t) {
                 mbar_init(&s_full[t], 1);
-                mbar_init(&p_full[t], BQ);
+                mbar_init(&p_full[t], 4);
                 mbar_init(&o_done[t], 1);
             }
             fence_mbar_init();
@@ -143,8 +145,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
             __syncwarp();
             for (int j = 0; j < n_blocks; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
+                const int st = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
                 const bool tail = j >= n_full;
                 const uint32_t bytes = tail ? tail_rows * HD * 2 : KV_BYTES;
                 const int atom_stride = tail ? tail_rows * 128 : KV_ATOM;  // the tail box is shorter, atoms pack tighter
@@ -175,10 +177,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         {
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             auto issue_qk = [&](int t, int j) {
-                const int st = j & 1;
+                const int st = j % STAGES;
                 const int kv = j >= n_full ? tail_rows : BKV;
                 if (t == 0) {
-                    mbar_wait(&k_full[st], (j >> 1) & 1);
+                    mbar_wait(&k_full[st], (j / STAGES) & 1);
                     tc_fence_after();
                 }
                 const uint32_t q_addr = smem_u32(smem + OFF_Q + t * Q_BYTES);
@@ -201,11 +203,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_wait(q_full, 0);
             for (int t = 0; t < n_tiles; ++t) issue_qk(t, 0);
             for (int j = 0; j < n_blocks; ++j) {
-                const int st = j & 1;
+                const int st = j % STAGES;
                 const int kv = j >= n_full ? tail_rows : BKV;
                 for (int t = 0; t < n_tiles; ++t) {
-                    mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in smem, O(t) rescaled if it had to be
-                    if (t == 0) mbar_wait(&v_full[st], (j >> 1) & 1);
+                    mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in TMEM, O(t) rescaled if it had to be
+                    if (t == 0) mbar_wait(&v_full[st], (j / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t tm_p = tmem_u + t * TM_TILE;  // P_j: bf16 pairs in the first 32 columns of the S block
                     const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
@@ -341,7 +343,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     l_run += (s0 + s1) + (s2 + s3);
                 }
                 tc_fence_before();
-                mbar_arrive(&p_full[t]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[t]);  // one arrival per softmax warp
             }
 
             mbar_wait(&o_done[t], 0);
