@@ -61,7 +61,7 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
     }
     if (kGelu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = gelu_erf(x[j]);
+        for (int j = 0; j < 32; j += 2) gelu_erf2(x[j], x[j + 1]);
     }
     if (ep.colscale) {
 #pragma unroll
