@@ -199,11 +199,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
             const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * SLICE_COLS;
             const int colb = n_blk * BN + slice * SLICE_COLS;
-            // 32 accumulator columns -> bias / GELU / scale in fp32 (in place)
+            // 32 accumulator columns -> bias / GELU / scale in fp32 (in place). The accumulator stage is handed back to
+            // the MMA warp as soon as this warp's LAST tcgen05.ld of the tile has completed, before the math and stores.
             auto load32 = [&](int c, float (&x)[32]) {
                 uint32_t v[32];
                 tmem_ld_32x32(tm + c, v);
                 tmem_ld_wait();
+                if (c + 32 == SLICE_COLS) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
                 if (colb + c < N) epilogue_math<kGelu>(x, colb + c, ep);
@@ -250,9 +256,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     flush(packed, colb + c);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }

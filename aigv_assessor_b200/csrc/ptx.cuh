@@ -83,8 +83,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Default semantics (.release at .cta scope), as CUTLASS's ClusterBarrier::arrive(cta_id): an explicit .release.cluster
+// compiles to MEMBAR.ALL.CTA + ERRBAR + SYNCS.ARRIVE.RED and was 20-30% of the GEMM epilogue warps' stall samples. What
+// this arrive orders are tcgen05.ld reads against later tcgen05.mma writes, which tcgen05.fence::before_thread_sync covers.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 // 2-CTA TMA load: data lands in THIS CTA's smem, the transaction bytes are credited to the mbarrier at the same offset
 // in the pair's leader (even) CTA (peer bit 24 of the shared::cluster address cleared).
