@@ -176,24 +176,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         // released by the commit that follows its last reader (the last live tile).
         {
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            // Base descriptors are built once; every MMA step derives its operands with one add (the descriptor
+            // bit-twiddling per UTCHMMA was most of this warp's instruction stream, and this warp is the critical path).
+            const uint64_t q_desc0 = umma_desc_sw128(smem_u32(smem + OFF_Q), 16, 1024);
+            const uint64_t k_desc0 = umma_desc_sw128(smem_u32(smem + OFF_K), 16, 1024);
+            const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + OFF_V), KV_ATOM, 1024);
+            const uint64_t v_desc0_tail = umma_desc_sw128(smem_u32(smem + OFF_V), tail_rows * 128, 1024);
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+            const uint32_t idesc_qk_tail = umma_idesc_bf16(BQ, tail_rows, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
             auto issue_qk = [&](int t, int j) {
                 const int st = j % STAGES;
-                const int kv = j >= n_full ? tail_rows : BKV;
+                const bool tail = j >= n_full;
                 if (t == 0) {
                     mbar_wait(&k_full[st], (j / STAGES) & 1);
                     tc_fence_after();
                 }
-                const uint32_t q_addr = smem_u32(smem + OFF_Q + t * Q_BYTES);
-                const uint32_t k_addr = smem_u32(smem + OFF_K + st * KV_BYTES);
-                const uint32_t k_atom = j >= n_full ? tail_rows * 128 : KV_ATOM;
-                const uint32_t idesc = umma_idesc_bf16(BQ, kv, 0, 0);
+                const uint64_t qd = umma_desc_advance(q_desc0, t * Q_BYTES);
+                const uint64_t kd = umma_desc_advance(k_desc0, st * KV_BYTES);
+                const uint32_t k_atom = tail ? tail_rows * 128 : KV_ATOM;
+                const uint32_t idesc = tail ? idesc_qk_tail : idesc_qk;
                 const uint32_t tm_s = tmem_u + t * TM_TILE;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < HD / 16; ++k) {  // d axis: 4 steps of 32 B inside each 64-column atom
-                        umma_bf16_ss(tm_s, umma_desc_sw128(q_addr + (k >> 2) * Q_ATOM + (k & 3) * 32, 16, 1024),
-                                     umma_desc_sw128(k_addr + (k >> 2) * k_atom + (k & 3) * 32, 16, 1024), idesc,
-                                     k != 0 ? 1u : 0u);
+                        umma_bf16_ss(tm_s, umma_desc_advance(qd, (k >> 2) * Q_ATOM + (k & 3) * 32),
+                                     umma_desc_advance(kd, (k >> 2) * k_atom + (k & 3) * 32), idesc, k != 0 ? 1u : 0u);
                     }
                     umma_commit(&s_full[t]);
                     if (t == n_tiles - 1) umma_commit(&k_empty[st]);
@@ -204,20 +212,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             for (int t = 0; t < n_tiles; ++t) issue_qk(t, 0);
             for (int j = 0; j < n_blocks; ++j) {
                 const int st = j % STAGES;
-                const int kv = j >= n_full ? tail_rows : BKV;
+                const bool tail = j >= n_full;
+                const int ksteps = (tail ? tail_rows : BKV) / 16;
+                const uint64_t vd = umma_desc_advance(tail ? v_desc0_tail : v_desc0, st * KV_BYTES);
                 for (int t = 0; t < n_tiles; ++t) {
                     mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in TMEM, O(t) rescaled if it had to be
                     if (t == 0) mbar_wait(&v_full[st], (j / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t tm_p = tmem_u + t * TM_TILE;  // P_j: bf16 pairs in the first 32 columns of the S block
-                    const uint32_t v_addr = smem_u32(smem + OFF_V + st * KV_BYTES);
-                    const uint32_t tm_o = tmem_u + t * TM_TILE + TM_O;
-                    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
-                    const uint32_t v_lbo = j >= n_full ? tail_rows * 128 : KV_ATOM;  // stride between 64-column atoms
+                    const uint32_t tm_o = tm_p + TM_O;
                     if (elect_one()) {
-                        for (int k = 0; k < kv / 16; ++k) {
+                        for (int k = 0; k < ksteps; ++k) {
                             // A = P_j from TMEM: 8 columns (16 keys) per step; B = V rows [16k,16k+16): 2 KiB apart
-                            umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_sw128(v_addr + k * 2048, v_lbo, 1024), idesc_pv,
+                            umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv,
                                          (j | k) != 0 ? 1u : 0u);
                         }
                         if (t == n_tiles - 1) umma_commit(&v_empty[st]);
@@ -298,7 +305,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     }
                     // pass 2: probabilities -> bf16 pairs, row sum (independent chains); P then overwrites S in TMEM
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    uint32_t pk[32];  // 64 probabilities of this row, two per register (even key in the low half)
                     if (!tail) {
                         // packed fp32x2 arithmetic (FFMA2 / FADD2): one issue slot per two keys for the scale and the sum
                         const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_ref, -m_ref);
@@ -308,6 +314,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                             uint32_t v[32];
                             tmem_ld_32x32(tm_s + c, v);
                             tmem_ld_wait();
+                            uint32_t pk[16];  // 32 probabilities, two per register (even key in the low half)
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
                                 float x0, x1, x2, x3;
@@ -316,13 +323,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                                 const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
                                 sum01 = add2(sum01, pack2(p0, p1));
                                 sum23 = add2(sum23, pack2(p2, p3));
-                                pk[(c + i) >> 1] = pack_bf16x2(p0, p1);
-                                pk[((c + i) >> 1) + 1] = pack_bf16x2(p2, p3);
+                                pk[i >> 1] = pack_bf16x2(p0, p1);
+                                pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
                             }
+                            // P columns [c/2, c/2+16) overwrite S columns that this thread has already consumed
+                            tmem_st_32x16(tm_s + (c >> 1), pk);
                         }
                         unpack2(sum01, s0, s1);
                         unpack2(sum23, s2, s3);
-                        tmem_st_32x32(tm_s, pk);
                     } else {
                         uint32_t v[32];  // tail_rows == 32 columns (attention_tail_rows caps the ragged block)
                         tmem_ld_32x32(tm_s, v);

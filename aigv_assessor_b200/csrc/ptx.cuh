@@ -259,6 +259,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
     return d;
 }
 
+// Same descriptor, `bytes` further into the tile (bytes % 16 == 0; stays inside the 14-bit address field).
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1  [15] a_major  [16] b_major (0=K,1=MN)
 //   [17,23) N>>3   [24,29) M>>4
