@@ -185,53 +185,64 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
             const uint32_t idesc_qk_tail = umma_idesc_bf16(BQ, tail_rows, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
-            auto issue_qk = [&](int t, int j) {
-                const int st = j % STAGES;
-                const bool tail = j >= n_full;
-                if (t == 0) {
-                    mbar_wait(&k_full[st], (j / STAGES) & 1);
-                    tc_fence_after();
-                }
+            // Q K^T of block j for tile t (operands must already be resident); called inside an elected region.
+            auto qk_mmas = [&](int t, int st, bool tail) {
                 const uint64_t qd = umma_desc_advance(q_desc0, t * Q_BYTES);
                 const uint64_t kd = umma_desc_advance(k_desc0, st * KV_BYTES);
                 const uint32_t k_atom = tail ? tail_rows * 128 : KV_ATOM;
                 const uint32_t idesc = tail ? idesc_qk_tail : idesc_qk;
                 const uint32_t tm_s = tmem_u + t * TM_TILE;
-                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {  // d axis: 4 steps of 32 B inside each 64-column atom
-                        umma_bf16_ss(tm_s, umma_desc_advance(qd, (k >> 2) * Q_ATOM + (k & 3) * 32),
-                                     umma_desc_advance(kd, (k >> 2) * k_atom + (k & 3) * 32), idesc, k != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&s_full[t]);
-                    if (t == n_tiles - 1) umma_commit(&k_empty[st]);
+                for (int k = 0; k < HD / 16; ++k) {  // d axis: 4 steps of 32 B inside each 64-column atom
+                    umma_bf16_ss(tm_s, umma_desc_advance(qd, (k >> 2) * Q_ATOM + (k & 3) * 32),
+                                 umma_desc_advance(kd, (k >> 2) * k_atom + (k & 3) * 32), idesc, k != 0 ? 1u : 0u);
                 }
-                __syncwarp();
+                umma_commit(&s_full[t]);
+                if (t == n_tiles - 1) umma_commit(&k_empty[st]);
             };
             mbar_wait(q_full, 0);
-            for (int t = 0; t < n_tiles; ++t) issue_qk(t, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            if (elect_one()) {
+                for (int t = 0; t < n_tiles; ++t) qk_mmas(t, 0, n_full == 0);
+            }
+            __syncwarp();
             for (int j = 0; j < n_blocks; ++j) {
                 const int st = j % STAGES;
+                const int st1 = (j + 1) % STAGES;
                 const bool tail = j >= n_full;
+                const bool more = j + 1 < n_blocks;
+                const bool tail1 = j + 1 >= n_full;
                 const int ksteps = (tail ? tail_rows : BKV) / 16;
                 const uint64_t vd = umma_desc_advance(tail ? v_desc0_tail : v_desc0, st * KV_BYTES);
                 for (int t = 0; t < n_tiles; ++t) {
                     mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in TMEM, O(t) rescaled if it had to be
-                    if (t == 0) mbar_wait(&v_full[st], (j / STAGES) & 1);
+                    if (t == 0) {
+                        mbar_wait(&v_full[st], (j / STAGES) & 1);
+                        if (more) mbar_wait(&k_full[st1], ((j + 1) / STAGES) & 1);
+                    }
                     tc_fence_after();
                     const uint32_t tm_p = tmem_u + t * TM_TILE;  // P_j: bf16 pairs in the first 32 columns of the S block
                     const uint32_t tm_o = tm_p + TM_O;
+                    // one elected region per (tile, block): O += P_j V_j, its commits, then S = Q K_{j+1}^T whose
+                    // s_full commit also covers the P V just issued
                     if (elect_one()) {
-                        for (int k = 0; k < ksteps; ++k) {
-                            // A = P_j from TMEM: 8 columns (16 keys) per step; B = V rows [16k,16k+16): 2 KiB apart
-                            umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv,
-                                         (j | k) != 0 ? 1u : 0u);
+                        if (!tail) {
+#pragma unroll
+                            for (int k = 0; k < BKV / 16; ++k)
+                                // A = P_j from TMEM: 8 columns (16 keys) per step; B = V rows [16k,16k+16): 2 KiB apart
+                                umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv,
+                                             (j | k) != 0 ? 1u : 0u);
+                        } else {
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv,
+                                             (j | k) != 0 ? 1u : 0u);
                         }
                         if (t == n_tiles - 1) umma_commit(&v_empty[st]);
-                        if (j + 1 == n_blocks) umma_commit(&o_done[t]);
+                        if (more) qk_mmas(t, st1, tail1);
+                        else umma_commit(&o_done[t]);
                     }
                     __syncwarp();
-                    if (j + 1 < n_blocks) issue_qk(t, j + 1);  // its s_full commit also covers P_j V_j of this tile
                 }
             }
         }
