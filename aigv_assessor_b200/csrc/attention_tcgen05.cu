@@ -8,7 +8,7 @@
 // by TMA (no split / permute copies); channel order (three, head, d) as in modeling_intern_vit.py:164. Both query tiles
 // consume every K/V stage, which halves the K/V tile traffic from L2 (measured to be the first bound of a
 // one-tile-per-CTA kernel: ~5.9 TB/s of tile loads with the softmax math removed).
-//   warp 8: TMA producer (Q tiles once; K/V ring, 64 keys per block) + MMA issuer of tile 1   warp 9: MMA issuer of tile 0
+//   warp 8: TMA producer (Q tiles once; K and V double buffered, 64 keys per block)   warp 9: MMA issuer (one thread)
 //   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, one query row per thread (TMEM lane == row, so row max /
 //   sum need no shuffles). The two warpgroups ping-pong against the single MMA thread: while one does its exp work the
 //   tensor core runs the other's P V and next Q K^T.
@@ -113,9 +113,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_init(q_full, 1);
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&k_full[s], 1);
-                mbar_init(&k_empty[s], n_tiles);  // released by the Q K^T commit of every live tile
+                mbar_init(&k_empty[s], 1);
                 mbar_init(&v_full[s], 1);
-                mbar_init(&v_empty[s], n_tiles);  // released by the P V commit of every live tile
+                mbar_init(&v_empty[s], 1);
             }
             for (int t = 0; t < TILES; ++t) {
                 mbar_init(&s_full[t], 1);
@@ -133,115 +133,118 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= SOFTMAX_WARPS) {
-        // ------------------------------------------------------------ issuing warps
-        // warp 9: MMA issuer of query tile 0.  warp 8: TMA producer AND MMA issuer of query tile 1 (the producer is idle
-        // most of the time; a dedicated issuer per tile removes the head-of-line coupling between the two tiles and
-        // halves the instruction stream of what is this kernel's critical path). K/V are prefetched STAGES-1 blocks ahead:
-        // the stage being refilled was last read by MMAs issued a whole block earlier, so the producer's waits are short.
-        // Both warps run converged; single instructions are predicated on one elected lane (inside a divergent
-        // `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT/BRA.U.ANY loop with R2UR transfers).
-        const bool is_producer = warp == SOFTMAX_WARPS;
-        const int t = is_producer ? 1 : 0;
-        const bool has_tile = t < n_tiles;
-        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        // Base descriptors are built once; every MMA step derives its operands with one add.
-        const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + OFF_Q + t * Q_BYTES), 16, 1024);
-        const uint64_t k_desc0 = umma_desc_sw128(smem_u32(smem + OFF_K), 16, 1024);
-        const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + OFF_V), KV_ATOM, 1024);
-        const uint64_t v_desc0_tail = umma_desc_sw128(smem_u32(smem + OFF_V), tail_rows * 128, 1024);
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
-        const uint32_t idesc_qk_tail = umma_idesc_bf16(BQ, tail_rows, 0, 0);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
-        const uint32_t tm_p = tmem_u + t * TM_TILE;  // S block, later P_j (bf16 pairs in its first 32 columns)
-        const uint32_t tm_o = tm_p + TM_O;
-
-        auto load_block = [&](int jb) {
-            const int st = jb % STAGES;
-            const uint32_t ph = (jb / STAGES) & 1;
-            const bool tail = jb >= n_full;
-            const uint32_t bytes = tail ? tail_rows * HD * 2 : KV_BYTES;
-            const int atom_stride = tail ? tail_rows * 128 : KV_ATOM;  // the tail box is shorter, atoms pack tighter
-            const CUtensorMap* tm = tail ? &tm_tail : &tm_kv;
-            const int r = row_base + jb * BKV;
-            mbar_wait(&k_empty[st], ph ^ 1);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&k_full[st], bytes);
-                for (int a = 0; a < ATOMS; ++a)
-                    tma_load_2d(smem + OFF_K + st * KV_BYTES + a * atom_stride, tm, &k_full[st], D + head * HD + a * 64, r);
-            }
-            __syncwarp();
-            mbar_wait(&v_empty[st], ph ^ 1);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(&v_full[st], bytes);
-                for (int a = 0; a < ATOMS; ++a)
-                    tma_load_2d(smem + OFF_V + st * KV_BYTES + a * atom_stride, tm, &v_full[st],
-                                2 * D + head * HD + a * 64, r);
-            }
-            __syncwarp();
-        };
-        // Q K^T of block jb for this warp's tile (operands resident); called inside an elected region.
-        auto qk_mmas = [&](int st, bool tail) {
-            const uint64_t kd = umma_desc_advance(k_desc0, st * KV_BYTES);
-            const uint32_t k_atom = tail ? tail_rows * 128 : KV_ATOM;
-            const uint32_t idesc = tail ? idesc_qk_tail : idesc_qk;
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) {  // d axis: 4 steps of 32 B inside each 64-column atom
-                umma_bf16_ss(tm_p, umma_desc_advance(q_desc, (k >> 2) * Q_ATOM + (k & 3) * 32),
-                             umma_desc_advance(kd, (k >> 2) * k_atom + (k & 3) * 32), idesc, k != 0 ? 1u : 0u);
-            }
-            umma_commit(&s_full[t]);
-            umma_commit(&k_empty[st]);  // one arrival per live tile
-        };
-
-        if (is_producer) {
+    if (warp == SOFTMAX_WARPS) {
+        // ------------------------------------------------------------ TMA producer
+        {
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, n_tiles * Q_BYTES);
-                for (int tt = 0; tt < n_tiles; ++tt)
+                for (int t = 0; t < n_tiles; ++t)
                     for (int a = 0; a < ATOMS; ++a)
-                        tma_load_2d(smem + OFF_Q + tt * Q_BYTES + a * Q_ATOM, &tm_q, q_full, head * HD + a * 64,
-                                    row_base + q0 + tt * BQ);
+                        tma_load_2d(smem + OFF_Q + t * Q_BYTES + a * Q_ATOM, &tm_q, q_full, head * HD + a * 64,
+                                    row_base + q0 + t * BQ);
             }
             __syncwarp();
-            for (int jb = 0; jb < STAGES - 1 && jb < n_blocks; ++jb) load_block(jb);
+            for (int j = 0; j < n_blocks; ++j) {
+                const int st = j % STAGES;
+                const uint32_t ph = (j / STAGES) & 1;
+                const bool tail = j >= n_full;
+                const uint32_t bytes = tail ? tail_rows * HD * 2 : KV_BYTES;
+                const int atom_stride = tail ? tail_rows * 128 : KV_ATOM;  // the tail box is shorter, atoms pack tighter
+                const CUtensorMap* tm = tail ? &tm_tail : &tm_kv;
+                const int r = row_base + j * BKV;
+                mbar_wait(&k_empty[st], ph ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&k_full[st], bytes);
+                    for (int a = 0; a < ATOMS; ++a)
+                        tma_load_2d(smem + OFF_K + st * KV_BYTES + a * atom_stride, tm, &k_full[st],
+                                    D + head * HD + a * 64, r);
+                }
+                __syncwarp();
+                mbar_wait(&v_empty[st], ph ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&v_full[st], bytes);
+                    for (int a = 0; a < ATOMS; ++a)
+                        tma_load_2d(smem + OFF_V + st * KV_BYTES + a * atom_stride, tm, &v_full[st],
+                                    2 * D + head * HD + a * 64, r);
+                }
+                __syncwarp();
+            }
         }
-        if (has_tile) {
+    } else if (warp == SOFTMAX_WARPS + 1) {
+        // ------------------------------------------------------------ MMA issuer
+        // Per block j and tile t (in order): wait P_j(t) -> O(t) += P_j V_j -> S(t) = Q(t) K_{j+1}^T. A K/V stage is
+        // released by the commit that follows its last reader (the last live tile).
+        {
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            // Base descriptors are built once; every MMA step derives its operands with one add (the descriptor
+            // bit-twiddling per UTCHMMA was most of this warp's instruction stream, and this warp is the critical path).
+            const uint64_t q_desc0 = umma_desc_sw128(smem_u32(smem + OFF_Q), 16, 1024);
+            const uint64_t k_desc0 = umma_desc_sw128(smem_u32(smem + OFF_K), 16, 1024);
+            const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + OFF_V), KV_ATOM, 1024);
+            const uint64_t v_desc0_tail = umma_desc_sw128(smem_u32(smem + OFF_V), tail_rows * 128, 1024);
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+            const uint32_t idesc_qk_tail = umma_idesc_bf16(BQ, tail_rows, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
+            // Q K^T of block j for tile t (operands must already be resident); called inside an elected region.
+            auto qk_mmas = [&](int t, int st, bool tail) {
+                const uint64_t qd = umma_desc_advance(q_desc0, t * Q_BYTES);
+                const uint64_t kd = umma_desc_advance(k_desc0, st * KV_BYTES);
+                const uint32_t k_atom = tail ? tail_rows * 128 : KV_ATOM;
+                const uint32_t idesc = tail ? idesc_qk_tail : idesc_qk;
+                const uint32_t tm_s = tmem_u + t * TM_TILE;
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {  // d axis: 4 steps of 32 B inside each 64-column atom
+                    umma_bf16_ss(tm_s, umma_desc_advance(qd, (k >> 2) * Q_ATOM + (k & 3) * 32),
+                                 umma_desc_advance(kd, (k >> 2) * k_atom + (k & 3) * 32), idesc, k != 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[t]);
+                if (t == n_tiles - 1) umma_commit(&k_empty[st]);
+            };
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
-            if (elect_one()) qk_mmas(0, n_full == 0);
-            __syncwarp();
-        }
-        for (int j = 0; j < n_blocks; ++j) {
-            if (is_producer && j + STAGES - 1 < n_blocks) load_block(j + STAGES - 1);
-            if (!has_tile) continue;
-            const int st = j % STAGES;
-            const int st1 = (j + 1) % STAGES;
-            const bool tail = j >= n_full;
-            const bool more = j + 1 < n_blocks;
-            const int ksteps = (tail ? tail_rows : BKV) / 16;
-            const uint64_t vd = umma_desc_advance(tail ? v_desc0_tail : v_desc0, st * KV_BYTES);
-            mbar_wait(&p_full[t], j & 1);  // S_j consumed, P_j in TMEM, O rescaled if it had to be
-            mbar_wait(&v_full[st], (j / STAGES) & 1);
-            if (more) mbar_wait(&k_full[st1], ((j + 1) / STAGES) & 1);
-            tc_fence_after();
-            // one elected region per block: O += P_j V_j, its commits, then S = Q K_{j+1}^T whose s_full commit also
-            // covers the P V just issued
             if (elect_one()) {
-                if (!tail) {
-#pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)
-                        // A = P_j from TMEM: 8 columns (16 keys) per step; B = V rows [16k,16k+16): 2 KiB apart
-                        umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv, (j | k) != 0 ? 1u : 0u);
-                } else {
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv, (j | k) != 0 ? 1u : 0u);
-                }
-                umma_commit(&v_empty[st]);  // one arrival per live tile
-                if (more) qk_mmas(st1, j + 1 >= n_full);
-                else umma_commit(&o_done[t]);
+                for (int t = 0; t < n_tiles; ++t) qk_mmas(t, 0, n_full == 0);
             }
             __syncwarp();
+            for (int j = 0; j < n_blocks; ++j) {
+                const int st = j % STAGES;
+                const int st1 = (j + 1) % STAGES;
+                const bool tail = j >= n_full;
+                const bool more = j + 1 < n_blocks;
+                const bool tail1 = j + 1 >= n_full;
+                const int ksteps = (tail ? tail_rows : BKV) / 16;
+                const uint64_t vd = umma_desc_advance(tail ? v_desc0_tail : v_desc0, st * KV_BYTES);
+                for (int t = 0; t < n_tiles; ++t) {
+                    mbar_wait(&p_full[t], j & 1);  // S_j(t) consumed, P_j(t) in TMEM, O(t) rescaled if it had to be
+                    if (t == 0) {
+                        mbar_wait(&v_full[st], (j / STAGES) & 1);
+                        if (more) mbar_wait(&k_full[st1], ((j + 1) / STAGES) & 1);
+                    }
+                    tc_fence_after();
+                    const uint32_t tm_p = tmem_u + t * TM_TILE;  // P_j: bf16 pairs in the first 32 columns of the S block
+                    const uint32_t tm_o = tm_p + TM_O;
+                    // one elected region per (tile, block): O += P_j V_j, its commits, then S = Q K_{j+1}^T whose
+                    // s_full commit also covers the P V just issued
+                    if (elect_one()) {
+                        if (!tail) {
+#pragma unroll
+                            for (int k = 0; k < BKV / 16; ++k)
+                                // A = P_j from TMEM: 8 columns (16 keys) per step; B = V rows [16k,16k+16): 2 KiB apart
+                                umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv,
+                                             (j | k) != 0 ? 1u : 0u);
+                        } else {
+                            for (int k = 0; k < ksteps; ++k)
+                                umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv,
+                                             (j | k) != 0 ? 1u : 0u);
+                        }
+                        if (t == n_tiles - 1) umma_commit(&v_empty[st]);
+                        if (more) qk_mmas(t, st1, tail1);
+                        else umma_commit(&o_done[t]);
+                    }
+                    __syncwarp();
+                }
+            }
         }
     } else {
         // ------------------------------------------------------------ softmax warpgroups: one query row per thread
