@@ -63,10 +63,10 @@ norm_f32_to_bf16_reg_kernel(const float* __restrict__ x, const float* __restrict
     float4 v[VPL];
     // lane owns float4 index (2*i)*32 + 2*lane + {0,1}: pairs of adjacent float4 -> one 16-byte bf16 store per pair
     if constexpr (VPL == 1) {
-        v[0] = xr[lane];
+        v[0] = __ldcs(xr + lane);
     } else {
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) v[i] = xr[(i >> 1) * 64 + 2 * lane + (i & 1)];
+        for (int i = 0; i < VPL; ++i) v[i] = __ldcs(xr + (i >> 1) * 64 + 2 * lane + (i & 1));  // streaming: read once
     }
     float mean = 0.f;
     if (!rms) {
