@@ -85,6 +85,12 @@ SIGNATURES = {
     "aigv_preprocess_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                      C.c_int, _P, _P, _P]),
     "aigv_gemm_epilogue": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "aigv_stats_slices": (C.c_int, [C.c_int]),
+    "aigv_fold_norm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "aigv_gemm_residual_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "aigv_gemm_norm_fused": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, _P]),
+    "aigv_assemble_tokens_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "aigv_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "aigv_rmsnorm_inplace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),

@@ -110,12 +110,16 @@ struct LayerW {
     __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
     float *qkv_b, *proj_b, *fc1_b, *fc2_b, *ls1, *ls2, *n1w, *n1b, *n2w, *n2b, *qnw, *knw;
     CUtensorMap tm_qkv, tm_proj, tm_fc1, tm_fc2;
+    // LayerNorm folded into the following Linear (fused schedule): W*gamma, its row sums, b + W beta
+    __nv_bfloat16 *qkv_wf, *fc1_wf;
+    float *qkv_wsum, *qkv_bf, *fc1_wsum, *fc1_bf;
+    CUtensorMap tm_qkv_f, tm_fc1_f;
 };
 
 struct ActMaps {
     int n = -1;
     CUtensorMap patches, xn, attn, h, ps, m1, qkv_q, qkv_kv, qkv_tail;   // TMA loads (GEMM A operands, attention)
-    CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out;              // TMA stores / reduce-adds (GEMM outputs)
+    CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out, xb_out;      // TMA stores / reduce-adds (GEMM outputs)
 };
 
 enum KClass { K_IM2COL = 0, K_GEMM_PATCH, K_ASSEMBLE, K_NORM, K_GEMM_QKV, K_QKNORM, K_ATTENTION, K_GEMM_PROJ,
@@ -159,6 +163,11 @@ struct aigv_handle {
     __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *patches = nullptr, *ps = nullptr,
                   *m1 = nullptr;
     ActMaps maps;
+    // LayerNorm-fused schedule (default; AIGV_FUSED_LN=0 selects the standalone norm kernels): the proj/fc2 epilogues
+    // produce the residual stream, its bf16 copy (in xn) and per-token statistics; qkv/fc1 apply the norm in theirs.
+    bool fused_ln = true;
+    int stat_parts = 0;          // D / gemm_stats_slice_cols(), rounded up
+    float2* stats = nullptr;     // [stat_parts][max_tiles * S]
     // front end
     float* lut = nullptr;
     std::map<std::tuple<int, int, int, int>, PlanDev> plans;
@@ -210,6 +219,7 @@ size_t workspace_bytes_for(const aigv_handle* h, int t) {
     b += Mp * h->kpad * 2;    // patches
     b += Mo * h->W4 * 2;      // ps
     b += Mo * h->C * 2;       // m1
+    b += M * h->stat_parts * 8;  // LayerNorm statistics
     return b;
 }
 
@@ -233,6 +243,7 @@ int build_act_maps(aigv_handle* h, int n) {
     r |= make_tmap_2d(&h->maps.qkv_out, h->qkv, 0, M, 3 * h->D, 3 * h->D, cr, cb);
     r |= make_tmap_2d(&h->maps.h_out, h->hbuf, 0, M, h->I, h->I, cr, cb);
     r |= make_tmap_2d(&h->maps.m1_out, h->m1, 0, Mo, h->C, h->C, cr, cb);
+    r |= make_tmap_2d(&h->maps.xb_out, h->xn, 0, M, h->D, h->D, cr, cb);
     if (r) return -1;
     h->maps.n = n;
     return 0;
@@ -309,6 +320,11 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
         return bad(AIGV_ERR_UNSUPPORTED, "hidden/intermediate/llm widths must be multiples of 32");
     h->num_sms = device_num_sms();
     h->max_tiles = cfg->max_tiles;
+    h->stat_parts = (h->D + gemm_stats_slice_cols() - 1) / gemm_stats_slice_cols();
+    {
+        const char* e = getenv("AIGV_FUSED_LN");
+        h->fused_ln = !(e && e[0] == '0') && (h->D % 64 == 0) && h->stat_parts <= 32;
+    }
 
     const size_t D = h->D, I = h->I, C = h->C;
     bool ok = true;
@@ -358,6 +374,12 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
         ok &= dev_alloc(h, &w.n2b, D, true);
         ok &= dev_alloc(h, &w.qnw, D);
         ok &= dev_alloc(h, &w.knw, D);
+        ok &= dev_alloc(h, &w.qkv_wf, 3 * D * D);
+        ok &= dev_alloc(h, &w.fc1_wf, I * D);
+        ok &= dev_alloc(h, &w.qkv_wsum, 3 * D);
+        ok &= dev_alloc(h, &w.qkv_bf, 3 * D);
+        ok &= dev_alloc(h, &w.fc1_wsum, I);
+        ok &= dev_alloc(h, &w.fc1_bf, I);
         if (!ok) break;
         const std::string lp = pre + "encoder.layers." + std::to_string(l) + ".";
         add_slot(h, lp + "ls1", w.ls1, D, false);
@@ -393,6 +415,7 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
         ok &= dev_alloc(h, &h->patches, Mp * h->kpad, true);
         ok &= dev_alloc(h, &h->ps, Mo * h->W4, true);
         ok &= dev_alloc(h, &h->m1, Mo * C, true);
+        ok &= dev_alloc(h, &h->stats, M * h->stat_parts, true);
         h->ws_bytes = workspace_bytes_for(h, h->max_tiles);
     }
     // front-end normalisation table: ((u/255) - mean)/std in fp32, as torchvision ToTensor + Normalize
@@ -470,7 +493,6 @@ int aigv_set_weight(aigv_handle* h, const char* name, const void* ptr, int dtype
 }
 
 int aigv_finalize_weights(aigv_handle* h, void* stream) {
-    (void)stream;
     if (!h) return AIGV_ERR_INVALID;
     for (auto& kv : h->slots)
         if (kv.second.required && !kv.second.set) return fail(h, AIGV_ERR_MISSING, "weight not set: " + kv.first);
@@ -484,8 +506,26 @@ int aigv_finalize_weights(aigv_handle* h, void* stream) {
         r |= make_tmap_bf16_2d(&w.tm_proj, w.proj_w, h->D, h->D, h->D, bb, bc);
         r |= make_tmap_bf16_2d(&w.tm_fc1, w.fc1_w, h->I, h->D, h->D, bb, bc);
         r |= make_tmap_bf16_2d(&w.tm_fc2, w.fc2_w, h->D, h->I, h->I, bb, bc);
+        r |= make_tmap_bf16_2d(&w.tm_qkv_f, w.qkv_wf, 3 * h->D, h->D, h->D, bb, bc);
+        r |= make_tmap_bf16_2d(&w.tm_fc1_f, w.fc1_wf, h->I, h->D, h->D, bb, bc);
     }
     if (r) return fail(h, AIGV_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix");
+    {
+        // fold norm1 into qkv and norm2 into fc1 (the un-folded weights stay: re-finalizing after a weight update is safe)
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const bool rms = h->cfg.norm_type == AIGV_RMS_NORM;
+        cudaError_t e = cudaSuccess;
+        for (auto& w : h->layers) {
+            if (e == cudaSuccess)
+                e = launch_fold_norm_into_linear(w.qkv_w, w.n1w, rms ? nullptr : w.n1b, h->cfg.qkv_bias ? w.qkv_b : nullptr,
+                                                 w.qkv_wf, w.qkv_wsum, w.qkv_bf, 3 * h->D, h->D, st);
+            if (e == cudaSuccess)
+                e = launch_fold_norm_into_linear(w.fc1_w, w.n2w, rms ? nullptr : w.n2b, w.fc1_b, w.fc1_wf, w.fc1_wsum,
+                                                 w.fc1_bf, h->I, h->D, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cuda_fail(h, e, "folding norm weights");
+    }
     h->finalized = true;
     return AIGV_OK;
 }
@@ -544,17 +584,36 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         AIGV_LAUNCH(K_GEMM_PATCH, run_gemm(h->maps.patches, h->tm_pe_w, h->maps.pe_out, Mp, D, h->kpad, ep, h->num_sms, st),
                     "patch-embed gemm");
     }
-    AIGV_LAUNCH(K_ASSEMBLE, launch_assemble_tokens(h->pe, h->cls, h->pos, h->x, n, h->P, D, st), "assemble tokens");
+    const bool fused = h->fused_ln;
+    const int parts = h->stat_parts;
+    if (fused)
+        AIGV_LAUNCH(K_ASSEMBLE, launch_assemble_tokens(h->pe, h->cls, h->pos, h->x, n, h->P, D, st, h->xn, h->stats, parts),
+                    "assemble tokens");
+    else
+        AIGV_LAUNCH(K_ASSEMBLE, launch_assemble_tokens(h->pe, h->cls, h->pos, h->x, n, h->P, D, st), "assemble tokens");
+    // Fused schedule: xn holds bf16(x) (not LN(x)); the qkv / fc1 epilogues apply the norm from the per-token statistics
+    // that assemble / proj / fc2 leave in h->stats, with gamma / beta folded into the weights at finalize.
+    auto ln_consumer = [&](GemmEpilogue& ep, const float* wsum) {
+        ep.ln_stats = h->stats; ep.ln_nparts = parts; ep.ln_wsum = rms ? nullptr : wsum;
+        ep.ln_inv_d = 1.0f / (float)D; ep.ln_eps = eps;
+    };
+    auto residual_producer = [&](GemmEpilogue& ep) {
+        ep.out_f32 = 1;
+        if (fused) { ep.fused_residual = 1; ep.stats_out = h->stats; }
+        else ep.accumulate = 1;
+    };
 
     for (int l = 0; l < h->L; ++l) {
         LayerW& w = h->layers[l];
         // V2 norm1 -> V3 qkv -> (V3b qk-norm) -> V4 attention -> V5 proj * ls1 + residual
-        AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n1w, rms ? nullptr : w.n1b, h->xn, M, D, eps, rms, st), "norm1");
+        if (!fused)
+            AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n1w, rms ? nullptr : w.n1b, h->xn, M, D, eps, rms, st), "norm1");
         {
             GemmEpilogue ep;
-            ep.bias = h->cfg.qkv_bias ? w.qkv_b : nullptr;
-            AIGV_LAUNCH(K_GEMM_QKV, run_gemm(h->maps.xn, w.tm_qkv, h->maps.qkv_out, M, 3 * D, D, ep, h->num_sms, st),
-                        "qkv gemm");
+            if (fused) { ep.bias = w.qkv_bf; ln_consumer(ep, w.qkv_wsum); }
+            else ep.bias = h->cfg.qkv_bias ? w.qkv_b : nullptr;
+            AIGV_LAUNCH(K_GEMM_QKV, run_gemm(h->maps.xn, fused ? w.tm_qkv_f : w.tm_qkv, h->maps.qkv_out, M, 3 * D, D, ep,
+                                             h->num_sms, st), "qkv gemm");
         }
         if (h->cfg.qk_normalization) {
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st), "q_norm");
@@ -564,23 +623,28 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
                  "attention");
         {
             GemmEpilogue ep;
-            ep.bias = w.proj_b; ep.colscale = w.ls1; ep.out_f32 = 1; ep.accumulate = 1;  // x += ls1 * (attn W^T + b)
-            AIGV_LAUNCH(K_GEMM_PROJ, run_gemm(h->maps.attn, w.tm_proj, h->maps.x_out, M, D, D, ep, h->num_sms, st),
-                        "proj gemm");
+            ep.bias = w.proj_b; ep.colscale = w.ls1;  // x += ls1 * (attn W^T + b)
+            residual_producer(ep);
+            AIGV_LAUNCH(K_GEMM_PROJ, launch_gemm(h->maps.attn, w.tm_proj, h->maps.x_out, M, D, D, ep, h->num_sms, st,
+                                                 &h->maps.xb_out), "proj gemm");
         }
         // V2 norm2 -> V6 fc1+GELU -> V7 fc2 * ls2 + residual
-        AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n2w, rms ? nullptr : w.n2b, h->xn, M, D, eps, rms, st), "norm2");
+        if (!fused)
+            AIGV_LAUNCH(K_NORM, launch_norm_f32_to_bf16(h->x, w.n2w, rms ? nullptr : w.n2b, h->xn, M, D, eps, rms, st), "norm2");
         {
             GemmEpilogue ep;
-            ep.bias = w.fc1_b; ep.gelu = 1;
-            AIGV_LAUNCH(K_GEMM_FC1, run_gemm(h->maps.xn, w.tm_fc1, h->maps.h_out, M, I, D, ep, h->num_sms, st),
-                        "fc1 gemm");
+            ep.gelu = 1;
+            if (fused) { ep.bias = w.fc1_bf; ln_consumer(ep, w.fc1_wsum); }
+            else ep.bias = w.fc1_b;
+            AIGV_LAUNCH(K_GEMM_FC1, run_gemm(h->maps.xn, fused ? w.tm_fc1_f : w.tm_fc1, h->maps.h_out, M, I, D, ep,
+                                             h->num_sms, st), "fc1 gemm");
         }
         {
             GemmEpilogue ep;
-            ep.bias = w.fc2_b; ep.colscale = w.ls2; ep.out_f32 = 1; ep.accumulate = 1;  // x += ls2 * (h W^T + b)
-            AIGV_LAUNCH(K_GEMM_FC2, run_gemm(h->maps.h, w.tm_fc2, h->maps.x_out, M, D, I, ep, h->num_sms, st),
-                        "fc2 gemm");
+            ep.bias = w.fc2_b; ep.colscale = w.ls2;  // x += ls2 * (h W^T + b)
+            residual_producer(ep);
+            AIGV_LAUNCH(K_GEMM_FC2, launch_gemm(h->maps.h, w.tm_fc2, h->maps.x_out, M, D, I, ep, h->num_sms, st,
+                                                &h->maps.xb_out), "fc2 gemm");
         }
     }
     // X1/X2 + mlp1[0]: drop cls, pixel shuffle, LayerNorm(4D) ; X3: mlp1[1]+GELU, mlp1[3]
@@ -769,6 +833,58 @@ int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias
     cudaError_t e = run_gemm(ta, tb, tc, M, N, K, ep, device_num_sms(), st);
     if (e == cudaErrorInvalidValue) return AIGV_ERR_INVALID;
     return e == cudaSuccess ? AIGV_OK : AIGV_ERR_CUDA;
+}
+
+int aigv_stats_slices(int N) { return N > 0 ? (N + gemm_stats_slice_cols() - 1) / gemm_stats_slice_cols() : 0; }
+
+int aigv_fold_norm(const void* w_bf16, const float* gamma, const float* beta, const float* bias, void* wf_bf16,
+                   float* wsum, float* bias_f, int N, int K, void* stream) {
+    if (!w_bf16 || !gamma || !wf_bf16 || !wsum || !bias_f) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_fold_norm_into_linear(static_cast<const __nv_bfloat16*>(w_bf16), gamma, beta, bias,
+                                           static_cast<__nv_bfloat16*>(wf_bf16), wsum, bias_f, N, K,
+                                           static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_gemm_residual_stats(const void* a_bf16, const void* w_bf16, const float* bias, const float* colscale,
+                             float* x_f32, void* xb_bf16, float* stats, int M, int N, int K, void* stream) {
+    if (!a_bf16 || !w_bf16 || !x_f32 || !xb_bf16 || !stats || M <= 0 || N <= 0 || K <= 0 || (N % 64) != 0)
+        return AIGV_ERR_INVALID;
+    CUtensorMap ta, tb, tc, tx;
+    if (make_tmap_bf16_2d(&ta, a_bf16, M, K, K, gemm_box_rows_a(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    if (make_tmap_bf16_2d(&tb, w_bf16, N, K, K, w_box_rows(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    if (make_tmap_2d(&tc, x_f32, 1, M, N, N, gemm_box_rows_c(), gemm_box_cols_c(true))) return AIGV_ERR_INVALID;
+    if (make_tmap_2d(&tx, xb_bf16, 0, M, N, N, gemm_box_rows_c(), gemm_box_cols_c(false))) return AIGV_ERR_INVALID;
+    GemmEpilogue ep;
+    ep.bias = bias; ep.colscale = colscale; ep.out_f32 = 1; ep.fused_residual = 1;
+    ep.stats_out = reinterpret_cast<float2*>(stats);
+    AIGV_TRY0(launch_gemm(ta, tb, tc, M, N, K, ep, device_num_sms(), static_cast<cudaStream_t>(stream), &tx));
+    return AIGV_OK;
+}
+
+int aigv_gemm_norm_fused(const void* a_bf16, const void* wf_bf16, const float* wsum, const float* bias_f,
+                         const float* stats, int nparts, int D, float eps, void* out_bf16, int M, int N, int K, int gelu,
+                         void* stream) {
+    if (!a_bf16 || !wf_bf16 || !stats || !out_bf16 || nparts <= 0 || D <= 0 || M <= 0 || N <= 0 || K <= 0)
+        return AIGV_ERR_INVALID;
+    CUtensorMap ta, tb, tc;
+    if (make_tmap_bf16_2d(&ta, a_bf16, M, K, K, gemm_box_rows_a(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    if (make_tmap_bf16_2d(&tb, wf_bf16, N, K, K, w_box_rows(), gemm_box_cols())) return AIGV_ERR_INVALID;
+    if (make_tmap_2d(&tc, out_bf16, 0, M, N, N, gemm_box_rows_c(), gemm_box_cols_c(false))) return AIGV_ERR_INVALID;
+    GemmEpilogue ep;
+    ep.bias = bias_f; ep.gelu = gelu;
+    ep.ln_stats = reinterpret_cast<const float2*>(stats); ep.ln_nparts = nparts; ep.ln_wsum = wsum;
+    ep.ln_inv_d = 1.0f / (float)D; ep.ln_eps = eps;
+    AIGV_TRY0(launch_gemm(ta, tb, tc, M, N, K, ep, device_num_sms(), static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_assemble_tokens_stats(const float* pe, const float* cls, const float* pos, float* x, void* xb_bf16,
+                               float* stats, int nparts, int n, int P, int D, void* stream) {
+    if (!pe || !cls || !pos || !x || !xb_bf16 || !stats) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_assemble_tokens(pe, cls, pos, x, n, P, D, static_cast<cudaStream_t>(stream),
+                                     static_cast<__nv_bfloat16*>(xb_bf16), reinterpret_cast<float2*>(stats), nparts));
+    return AIGV_OK;
 }
 
 int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int heads, int head_dim, float scale,

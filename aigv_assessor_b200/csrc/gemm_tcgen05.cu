@@ -36,22 +36,41 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STG_BYTES = 4096;
 constexpr uint32_t TMEM_COLS = 512;
 
-// Two shapes of the same kernel: the GELU epilogue is instruction-issue heavy and wants 16 epilogue warps (4 per SMSP)
-// at the price of one pipeline stage; the plain / residual epilogues are lighter and keep 8 warps and 6 stages.
-template <int kEpiWarps>
+// Shapes of the same kernel: the GELU epilogue is instruction-issue heavy and wants 16 epilogue warps (4 per SMSP) at the
+// price of one pipeline stage; the plain epilogues keep 8 warps and 6 stages; the fused-residual epilogue (kResid) needs
+// three staging tiles per warp (two fp32 tiles for the x_old prefetch / x_new store, one bf16 tile) and runs 4 stages.
+template <int kEpiWarps, bool kResid>
 struct Cfg {
     static constexpr int EPI_WARPS = kEpiWarps;          // multiple of 4: warp%4 = TMEM lane quadrant
     static constexpr int SLICES = kEpiWarps / 4;         // column slices of the 256-column tile
     static constexpr int SLICE_COLS = BN / SLICES;       // 64 or 128 columns per warp
-    static constexpr int STAGES = kEpiWarps == 16 ? 5 : 6;
+    static constexpr int STAGES = kResid ? 4 : (kEpiWarps == 16 ? 5 : 6);
     static constexpr int THREADS = (kEpiWarps + 2) * 32;
+    static constexpr int WARP_STG = kResid ? 3 * STG_BYTES : STG_BYTES;
     static constexpr int OFF_STG = STAGES * STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_STG + kEpiWarps * STG_BYTES;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr int OFF_BAR = OFF_STG + kEpiWarps * WARP_STG;
+    static constexpr int SMEM_BYTES = OFF_BAR + 512;     // 2*STAGES + 4 pipeline barriers, 2 per epilogue warp, TMEM slot
 };
 
+// acc -> [LayerNorm applied algebraically] -> + bias -> act -> * colscale, on 32 consecutive columns from col0.
+// LN fusion: the A operand was the un-normalised activation x (bf16) and W carries gamma, so
+//   LN(x) W^T = rstd * (x W'^T - mean * wsum) + (b + W beta),   wsum[n] = sum_k W'[n,k]
+// with the row's mean / rstd taken from the (sum, sum of squares) the producing GEMM accumulated.
 template <bool kGelu>
-__device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep) {
+__device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep, float mean, float rstd) {
+    if (ep.ln_stats) {
+        if (ep.ln_wsum) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(ep.ln_wsum + col0 + j));
+                x[j] = rstd * fmaf(-mean, w.x, x[j]); x[j + 1] = rstd * fmaf(-mean, w.y, x[j + 1]);
+                x[j + 2] = rstd * fmaf(-mean, w.z, x[j + 2]); x[j + 3] = rstd * fmaf(-mean, w.w, x[j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] *= rstd;
+        }
+    }
     if (ep.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -72,18 +91,20 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
     }
 }
 
-template <bool kGelu, bool kOutF32, int kEpiWarps>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<kEpiWarps>::THREADS, 1)
+template <bool kGelu, bool kOutF32, int kEpiWarps, bool kResid>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<kEpiWarps, kResid>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, int M, int N, int K, GemmEpilogue ep) {
-    using C = Cfg<kEpiWarps>;
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
+                    GemmEpilogue ep) {
+    using C = Cfg<kEpiWarps, kResid>;
     constexpr int EPI_WARPS = C::EPI_WARPS, STAGES = C::STAGES, OFF_STG = C::OFF_STG, OFF_BAR = C::OFF_BAR;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* xload_bar = tempty_bar + 2;  // [EPI_WARPS][2] (kResid): x_old staging tile landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xload_bar + 2 * EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -103,6 +124,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
+        if (kResid) tma_prefetch_desc(&tmX);
     }
     if (warp == EPI_WARPS + 1) {
         if (lane == 0) {
@@ -114,6 +136,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_init(&tfull_bar[s], 1);                // multicast commit
                 mbar_init(&tempty_bar[s], 2 * EPI_WARPS);   // leader: epilogue warps of both CTAs
             }
+            if (kResid)
+                for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&xload_bar[s], 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -185,22 +209,49 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int quad = warp & 3;
         const int slice = warp >> 2;  // column slice of the 256-column tile
         constexpr int SLICE_COLS = C::SLICE_COLS;
-        uint8_t* stg = smem + OFF_STG + warp * STG_BYTES;
-        uint8_t* my_row = stg + lane * 128;
+        uint8_t* stg = smem + OFF_STG + warp * C::WARP_STG;
         const int sw = lane & 7;
         const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
         const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+        uint32_t xphase = 0;  // kResid: parity bits of this warp's two x_old staging barriers
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
+            const int colb = n_blk * BN + slice * SLICE_COLS;
+            // kResid: x_old does not depend on the MMAs: start fetching this warp's first staging tile before waiting
+            auto issue_xload = [&](int c) {
+                if (lane == 0 && row0 < M && colb + c < N) {
+                    uint64_t* bar = &xload_bar[2 * warp + ((c >> 5) & 1)];
+                    mbar_arrive_expect_tx(bar, STG_BYTES);
+                    tma_load_2d(stg + ((c >> 5) & 1) * STG_BYTES, &tmC, bar, colb + c, row0);
+                }
+            };
+            if (kResid) {
+                if (lane == 0) tma_store_wait_read<0>();  // staging tiles of the previous output tile have been read out
+                __syncwarp();
+                issue_xload(0);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
             const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * SLICE_COLS;
-            const int colb = n_blk * BN + slice * SLICE_COLS;
-            // 32 accumulator columns -> bias / GELU / scale in fp32 (in place). The accumulator stage is handed back to
-            // the MMA warp as soon as this warp's LAST tcgen05.ld of the tile has completed, before the math and stores.
+            // LayerNorm-fused consumer: this thread's row statistics
+            float mean = 0.f, rstd = 1.f;
+            if (ep.ln_stats) {
+                const int row = row0 + lane;
+                float sx = 0.f, sq = 0.f;
+                if (row < M)
+                    for (int p = 0; p < ep.ln_nparts; ++p) {  // fixed order: results do not depend on scheduling
+                        const float2 st = __ldg(ep.ln_stats + static_cast<size_t>(p) * M + row);
+                        sx += st.x;
+                        sq += st.y;
+                    }
+                mean = ep.ln_wsum ? sx * ep.ln_inv_d : 0.f;
+                rstd = rsqrtf(fmaxf(sq * ep.ln_inv_d - mean * mean, 0.f) + ep.ln_eps);
+            }
+            // 32 accumulator columns -> (LN) / bias / GELU / scale in fp32 (in place). The accumulator stage is handed
+            // back to the MMA warp as soon as this warp's LAST tcgen05.ld of the tile has completed.
             auto load32 = [&](int c, float (&x)[32]) {
                 uint32_t v[32];
                 tmem_ld_32x32(tm + c, v);
@@ -212,9 +263,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                if (colb + c < N) epilogue_math<kGelu>(x, colb + c, ep);
+                if (colb + c < N) epilogue_math<kGelu>(x, colb + c, ep, mean, rstd);
             };
             auto flush = [&](const uint4 (&packed)[8], int col0) {
+                uint8_t* my_row = stg + lane * 128;
                 if (lane == 0) tma_store_wait_read<0>();  // previous TMA store has finished reading the staging tile
                 __syncwarp();
 #pragma unroll
@@ -227,7 +279,55 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tma_store_commit();
                 }
             };
-            if (kOutF32) {
+            if (kResid) {
+                // Fused residual producer: x_new = x_old + colscale * (acc + bias) computed here (x_old tiles arrive by
+                // TMA, double buffered), written back as fp32 (the residual stream) AND as bf16 (the next GEMM's A
+                // operand), with the row's (sum, sum of squares) accumulated for the LayerNorm the next GEMM applies.
+                float rs = 0.f, rq = 0.f;
+                uint8_t* btile = stg + 2 * STG_BYTES;  // bf16 staging: 32 rows x 64 columns
+#pragma unroll 1
+                for (int c = 0; c < SLICE_COLS; c += 32) {
+                    const int b = (c >> 5) & 1;
+                    uint8_t* frow = stg + b * STG_BYTES + lane * 128;
+                    if (c + 32 < SLICE_COLS) {
+                        // the other fp32 tile (and, on even chunks, the bf16 tile) must have been read out by their stores
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+                        issue_xload(c + 32);
+                    }
+                    float x[32];
+                    load32(c, x);
+                    if (!(row0 < M && colb + c < N)) continue;  // warp-uniform: nothing of this chunk is inside C
+                    mbar_wait(&xload_bar[2 * warp + b], (xphase >> b) & 1);
+                    xphase ^= 1u << b;
+                    uint4 pb[4];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4* slot = reinterpret_cast<uint4*>(frow + ((j ^ sw) << 4));
+                        const uint4 o = *slot;
+                        const float y0 = __uint_as_float(o.x) + x[4 * j], y1 = __uint_as_float(o.y) + x[4 * j + 1];
+                        const float y2 = __uint_as_float(o.z) + x[4 * j + 2], y3 = __uint_as_float(o.w) + x[4 * j + 3];
+                        rs += (y0 + y1) + (y2 + y3);
+                        rq += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
+                        *slot = make_uint4(__float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2), __float_as_uint(y3));
+                        if (j & 1) { pb[j >> 1].z = pack_bf16x2(y0, y1); pb[j >> 1].w = pack_bf16x2(y2, y3); }
+                        else { pb[j >> 1].x = pack_bf16x2(y0, y1); pb[j >> 1].y = pack_bf16x2(y2, y3); }
+                    }
+                    uint8_t* brow = btile + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(brow + (((4 * b + j) ^ sw) << 4)) = pb[j];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, stg + b * STG_BYTES, colb + c, row0);          // x_new, fp32
+                        if (b) tma_store_2d(&tmX, btile, colb + c - 32, row0);            // x_new, bf16 (64 columns)
+                        tma_store_commit();
+                    }
+                }
+                // per-row partial (sum, sum of squares) of this 128-column slice; the consumer adds the slices in order
+                if (ep.stats_out && row0 + lane < M && colb < N)
+                    ep.stats_out[static_cast<size_t>(colb / SLICE_COLS) * M + row0 + lane] = make_float2(rs, rq);
+            } else if (kOutF32) {
 #pragma unroll 1
                 for (int c = 0; c < SLICE_COLS; c += 32) {  // 32-column fp32 staging tiles (128 B rows)
                     float x[32];
@@ -270,21 +370,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <bool kGelu, bool kOutF32, int kEpiWarps>
-cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
-                            const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
-    constexpr int SMEM_BYTES = Cfg<kEpiWarps>::SMEM_BYTES, THREADS = Cfg<kEpiWarps>::THREADS;
-    auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32, kEpiWarps>;
+template <bool kGelu, bool kOutF32, int kEpiWarps, bool kResid>
+cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmX,
+                           int M, int N, int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+    using C = Cfg<kEpiWarps, kResid>;
+    auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32, kEpiWarps, kResid>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (tiles < pairs) pairs = tiles;
-    kern<<<2 * pairs, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, ep);
+    kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmX, M, N, K, ep);
     return cudaGetLastError();
 }
 
@@ -295,19 +395,25 @@ int gemm_box_rows_b() { return BNH; }
 int gemm_box_cols() { return BK; }
 int gemm_box_rows_c() { return 32; }
 int gemm_box_cols_c(bool out_f32) { return out_f32 ? 32 : 64; }
+int gemm_stats_slice_cols() { return Cfg<8, true>::SLICE_COLS; }
 
 cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
-                         const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
+                        const GemmEpilogue& ep, int num_sms, cudaStream_t stream, const CUtensorMap* tmX) {
     if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0) return cudaErrorInvalidValue;
     if (ep.accumulate && !ep.out_f32) return cudaErrorInvalidValue;
+    if (ep.fused_residual) {
+        // x_new = x_old + colscale*(acc+bias) in the SM; needs the bf16 copy map and 64-column-aligned N
+        if (!ep.out_f32 || ep.gelu || ep.accumulate || !tmX || (N % 64) != 0) return cudaErrorInvalidValue;
+        return launch_variant<false, true, 8, true>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
+    }
     // The GELU epilogue is instruction-issue heavy: 16 epilogue warps and 5 stages; everything else 8 warps and 6 stages
     // (measured: the fp32 reduce-add epilogue of proj does not gain from more warps: 948 vs 1016 TFLOP/s).
     if (ep.gelu) {
-        return ep.out_f32 ? launch_variant<true, true, 16>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream)
-                          : launch_variant<true, false, 16>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream);
+        return ep.out_f32 ? launch_variant<true, true, 16, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream)
+                          : launch_variant<true, false, 16, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
     }
-    if (ep.out_f32) return launch_variant<false, true, 8>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream);
-    return launch_variant<false, false, 8>(tmA, tmB, tmC, M, N, K, ep, num_sms, stream);
+    if (ep.out_f32) return launch_variant<false, true, 8, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    return launch_variant<false, false, 8, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
 }
 
 }  // namespace aigv

@@ -14,6 +14,19 @@ struct GemmEpilogue {
     int out_f32 = 0;                  // output element type of the C tensor map: fp32 (1) or bf16 (0)
     int accumulate = 0;               // fp32 only: C += result (TMA reduce-add; the in-place residual stream)
     int gelu = 0;                     // exact erf GELU after bias
+    // LayerNorm fusion, consumer side: A was the un-normalised activation (bf16) and W carries gamma;
+    //   out = rstd[m] * (acc - mean[m] * ln_wsum[n]) + bias[n]  with mean/rstd from ln_stats[m] = (sum, sum of squares).
+    //   ln_wsum == nullptr selects RMSNorm (no mean).
+    //   ln_stats is [ln_nparts][M]: per-row partial sums over column slices, added in slice order.
+    const float2* ln_stats = nullptr;
+    int ln_nparts = 0;
+    const float* ln_wsum = nullptr;
+    float ln_inv_d = 0.f, ln_eps = 0.f;
+    // LayerNorm fusion, producer side (fp32 C only): C_new = C_old + colscale * (acc + bias) is formed in the SM (C_old
+    // tiles arrive by TMA), stored back as fp32 AND as bf16 through the extra map, and (sum, sum of squares) of every
+    // row of C_new are written to stats_out[slice][M], one slice per gemm_stats_slice_cols() columns of C.
+    int fused_residual = 0;
+    float2* stats_out = nullptr;
 };
 
 // ---- TMA descriptors (host) -------------------------------------------------------------------------------------
@@ -33,8 +46,10 @@ int gemm_box_rows_b();
 int gemm_box_cols();
 int gemm_box_rows_c();
 int gemm_box_cols_c(bool out_f32);
+int gemm_stats_slice_cols();  // columns per statistics slice of the fused-residual epilogue
+// tmX (fused_residual only): bf16 copy of C, box [gemm_box_rows_c(), 64].
 cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
-                        const GemmEpilogue& ep, int num_sms, cudaStream_t stream);
+                        const GemmEpilogue& ep, int num_sms, cudaStream_t stream, const CUtensorMap* tmX = nullptr);
 
 // ---- attention -------------------------------------------------------------------------------------------------
 // qkv: bf16 [frames*S, 3*D] with channel order (three, head, d); out: bf16 [frames*S, D] (head-major channels).
@@ -58,8 +73,14 @@ cudaError_t launch_rmsnorm_bf16_inplace(__nv_bfloat16* x, const float* w, int ro
 cudaError_t launch_im2col(const __nv_bfloat16* pv, __nv_bfloat16* patches, int n, int img, int patch, int kpad,
                           cudaStream_t stream);
 // x[n, 0, :] = cls + pos[0]; x[n, 1+p, :] = pe[n*P + p, :] + pos[1+p]   (pe fp32 already has the conv bias)
+// With xb/stats (LayerNorm-fused schedule): also the bf16 copy of x and per-token (sum, sum of squares) in slice 0 of
+// stats[nparts][n*(P+1)] (remaining slices zeroed).
 cudaError_t launch_assemble_tokens(const float* pe, const float* cls, const float* pos, float* x, int n, int P, int D,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, __nv_bfloat16* xb = nullptr, float2* stats = nullptr,
+                                   int nparts = 0);
+// Wf = bf16(W * gamma) per column, wsum[n] = sum_k Wf[n,k], bf[n] = b[n] + sum_k W[n,k] beta[k]  (beta, b may be null)
+cudaError_t launch_fold_norm_into_linear(const __nv_bfloat16* W, const float* gamma, const float* beta, const float* b,
+                                         __nv_bfloat16* Wf, float* wsum, float* bf, int N, int K, cudaStream_t stream);
 // Drop cls, 2x2 pixel-shuffle (v2) and LayerNorm(4D): x fp32 [n, 1+g*g, D] -> y bf16 [n*(g/2)^2, 4D].
 cudaError_t launch_pixel_shuffle_ln(const float* x, const float* w, const float* b, __nv_bfloat16* y, int n, int g,
                                     int D, float eps, int apply_ln, cudaStream_t stream);

@@ -221,6 +221,64 @@ assemble_tokens_kernel(const float* __restrict__ pe, const float* __restrict__ c
     }
 }
 
+// Warp-per-token variant for the LayerNorm-fused schedule: besides the fp32 residual stream it writes the bf16 copy
+// the first qkv GEMM reads, and the token's (sum, sum of squares) into slice 0 of the statistics array (other slices 0).
+__global__ void __launch_bounds__(256)
+assemble_tokens_stats_kernel(const float* __restrict__ pe, const float* __restrict__ cls, const float* __restrict__ pos,
+                             float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats,
+                             int nparts, int n, int P, int D) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int M = n * (P + 1);
+    if (row >= M) return;
+    const int t = row % (P + 1), f = row / (P + 1);
+    const float* src = t == 0 ? cls : pe + (static_cast<size_t>(f) * P + (t - 1)) * D;
+    const float* ps = pos + static_cast<size_t>(t) * D;
+    float s = 0.f, q = 0.f;
+    for (int c = lane * 4; c < D; c += 128) {
+        float4 v = t == 0 ? __ldg(reinterpret_cast<const float4*>(src + c)) : __ldcs(reinterpret_cast<const float4*>(src + c));
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(ps + c));
+        v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+        s += (v.x + v.y) + (v.z + v.w);
+        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        *reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D + c) = v;
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(xb + static_cast<size_t>(row) * D + c) = o;
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane < nparts) stats[static_cast<size_t>(lane) * M + row] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
+// LayerNorm folded into the following Linear (run once per weight load):
+//   Wf[n,k] = bf16(W[n,k] * gamma[k]);  wsum[n] = sum_k Wf[n,k];  bf[n] = b[n] + sum_k W[n,k] * beta[k]
+// so that  LN(x) W^T + b  =  rstd * (x Wf^T - mean * wsum) + bf.  One warp per output feature n.
+__global__ void __launch_bounds__(256)
+fold_norm_into_linear_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, const float* __restrict__ b,
+                             __nv_bfloat16* __restrict__ Wf, float* __restrict__ wsum, float* __restrict__ bf, int N,
+                             int K) {
+    const int nrow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (nrow >= N) return;
+    float sw = 0.f, sb = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = __bfloat162float(W[static_cast<size_t>(nrow) * K + k]);
+        const __nv_bfloat16 wf = __float2bfloat16_rn(w * gamma[k]);
+        Wf[static_cast<size_t>(nrow) * K + k] = wf;
+        sw += __bfloat162float(wf);
+        if (beta) sb += w * beta[k];
+    }
+    sw = warp_sum(sw);
+    sb = warp_sum(sb);
+    if (lane == 0) {
+        wsum[nrow] = sw;
+        bf[nrow] = (b ? b[nrow] : 0.f) + sb;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pixel_shuffle_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                         __nv_bfloat16* __restrict__ y, int n, int g, int D, float eps, int apply_ln) {
@@ -356,10 +414,23 @@ cudaError_t launch_im2col(const __nv_bfloat16* pv, __nv_bfloat16* patches, int n
 }
 
 cudaError_t launch_assemble_tokens(const float* pe, const float* cls, const float* pos, float* x, int n, int P, int D,
-                                   cudaStream_t stream) {
+                                   cudaStream_t stream, __nv_bfloat16* xb, float2* stats, int nparts) {
     if (n <= 0 || (D % 4) != 0) return cudaErrorInvalidValue;
+    if (xb || stats) {
+        if (!xb || !stats || nparts < 1 || nparts > 32) return cudaErrorInvalidValue;
+        const int rows = n * (P + 1);
+        assemble_tokens_stats_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(pe, cls, pos, x, xb, stats, nparts, n, P, D);
+        return cudaGetLastError();
+    }
     const size_t total = static_cast<size_t>(n) * (P + 1) * (D / 4);
     assemble_tokens_kernel<<<grid_for(total, 256), 256, 0, stream>>>(pe, cls, pos, x, n, P, D);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold_norm_into_linear(const __nv_bfloat16* W, const float* gamma, const float* beta, const float* b,
+                                         __nv_bfloat16* Wf, float* wsum, float* bf, int N, int K, cudaStream_t stream) {
+    if (N <= 0 || K <= 0) return cudaErrorInvalidValue;
+    fold_norm_into_linear_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, gamma, beta, b, Wf, wsum, bf, N, K);
     return cudaGetLastError();
 }
 

@@ -103,6 +103,25 @@ int aigv_preprocess_u8(aigv_handle* h, const uint8_t* frames, int n, int H, int 
 int aigv_gemm_epilogue(const void* a_bf16, const void* w_bf16, const float* bias, const float* colscale,
                        const float* residual, float* out_f32, void* out_bf16, int M, int N, int K, int gelu,
                        void* stream);
+/* LayerNorm-fused schedule (DESIGN.md "LayerNorm fusion"): the norm in front of qkv / fc1 (modeling_intern_vit.py:
+ * 224-226 norm1/norm2) is never materialised. Producers (proj, fc2 and the token assembly) leave the fp32 residual
+ * stream, its bf16 copy and per-token (sum, sum of squares) slices; consumers apply mean/rstd in their epilogue with
+ * gamma/beta folded into the weights:  LN(x) W^T + b = rstd * (x Wf^T - mean * wsum) + bias_f.
+ *   aigv_stats_slices(N)     number of statistics slices a producer with N output columns writes
+ *   aigv_fold_norm           Wf = bf16(W * gamma), wsum[n] = sum_k Wf[n,k], bias_f = bias + W beta (beta/bias may be NULL)
+ *   aigv_gemm_residual_stats x += colscale * (A W^T + bias) in place; xb = bf16(x); stats[slices][M][2]
+ *   aigv_gemm_norm_fused     out = act(rstd * (A Wf^T - mean * wsum) + bias_f); wsum NULL = RMSNorm; D = normalised width
+ *   aigv_assemble_tokens_stats  aigv_assemble_tokens + xb + stats (slice 0 carries the sums, the others are zeroed) */
+int aigv_stats_slices(int N);
+int aigv_fold_norm(const void* w_bf16, const float* gamma, const float* beta, const float* bias, void* wf_bf16,
+                   float* wsum, float* bias_f, int N, int K, void* stream);
+int aigv_gemm_residual_stats(const void* a_bf16, const void* w_bf16, const float* bias, const float* colscale,
+                             float* x_f32, void* xb_bf16, float* stats, int M, int N, int K, void* stream);
+int aigv_gemm_norm_fused(const void* a_bf16, const void* wf_bf16, const float* wsum, const float* bias_f,
+                         const float* stats, int nparts, int D, float eps, void* out_bf16, int M, int N, int K, int gelu,
+                         void* stream);
+int aigv_assemble_tokens_stats(const float* pe, const float* cls, const float* pos, float* x, void* xb_bf16,
+                               float* stats, int nparts, int n, int P, int D, void* stream);
 /* qkv bf16 [frames*S, 3*heads*head_dim] (three, head, d) -> out bf16 [frames*S, heads*head_dim]. */
 int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int heads, int head_dim, float scale,
                    void* stream);
