@@ -111,10 +111,11 @@ def load(build_if_missing: bool = True):
         if not build_if_missing:
             raise AigvError(f"{LIB_PATH} is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
         build()
+    path = os.environ.get("AIGV_LIB", LIB_PATH)  # development: A/B a prebuilt variant of the same ABI
     try:
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
     except OSError as e:  # pragma: no cover
-        raise AigvError(f"cannot load {LIB_PATH}: {e}") from e
+        raise AigvError(f"cannot load {path}: {e}") from e
     for name, (res, args) in SIGNATURES.items():
         try:
             fn = getattr(lib, name)
