@@ -619,7 +619,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st), "q_norm");
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.knw, M, D, 3 * D, D, eps, st), "k_norm");
         }
-        AIGV_LAUNCH(K_ATTENTION, launch_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->attn, n, S, h->H, h->hd, scale, st),
+        AIGV_LAUNCH(K_ATTENTION, launch_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->qkv, h->attn, n, S, h->H, h->hd, scale, st),
                  "attention");
         {
             GemmEpilogue ep;
@@ -897,7 +897,7 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
     if (make_tmap_bf16_2d(&tq, qkv_bf16, M, D3, D3, attention_q_rows(), 64)) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tk, qkv_bf16, M, D3, D3, attention_kv_rows(), 64)) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tt, qkv_bf16, M, D3, D3, attention_tail_rows(S), 64)) return AIGV_ERR_INVALID;
-    AIGV_TRY0(launch_attention(tq, tk, tt, static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
+    AIGV_TRY0(launch_attention(tq, tk, tt, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
                                static_cast<cudaStream_t>(stream)));
     return AIGV_OK;
 }

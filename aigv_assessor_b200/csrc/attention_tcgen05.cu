@@ -21,8 +21,17 @@
 // tcgen05.ld/st) when the true running maximum exceeds it by more than 2^8, so p <= 256 always and the rescale is rare;
 // the final O / l is exact regardless of the reference point.
 // Resources: 64 KiB smem, 256 TMEM columns, <=102 registers -> 2 CTAs (16 softmax warps) per SM.
-// S = 1025 = 16*64 + 1: the ragged tail is one short KV block (32 columns, 1 valid, rest masked to -inf); on the query
-// side the last CTA of a (frame, head) holds the single leftover row and skips its empty second tile entirely.
+// S = 1025 = 16*64 + 1. On the KEY side a ragged tail of 2..32 keys is one short KV block (32 columns, invalid ones masked
+// to -inf); a tail of exactly ONE key (every ViT sequence: the class token makes S = 64k + 1) never enters the tensor
+// pipeline: the producer warp leaves that key's k and v rows in shared memory as fp32 and every query row folds it in
+// during its epilogue (one 64-term dot product against its own Q row, an exact max/alpha update, O += p v), which saves
+// one of the 17 block round trips. On the query
+// side a ViT sequence is (multiple of 256) + 1 (the class token): the one leftover query row would cost a whole extra
+// CTA per (frame, head) -- 20% of the grid for 0.1% of the rows. Instead ("side row" mode) the TMA producer warp of the
+// first CTA of each (frame, head) computes that row on the CUDA cores from the very K/V stages it has just loaded
+// (fp32 online softmax, one warp, ~700 instructions per 64-key block, hidden in the shadow of the tensor pipeline), and
+// the grid has exactly S/256 CTAs per (frame, head). Other sequence lengths keep the ceil(S/256) grid, where the last
+// CTA skips its empty second tile.
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -51,7 +60,9 @@ struct Geo {
     static constexpr int OFF_K = OFF_Q + TILES * Q_BYTES;   // STAGES stages
     static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES; // STAGES stages
     static constexpr int OFF_BAR = OFF_V + STAGES * KV_BYTES;
-    static constexpr int SMEM_BYTES = OFF_BAR + 256;        // 1 + 4*STAGES + 3*TILES mbarriers + the TMEM base slot
+    static constexpr int OFF_SIDE = OFF_BAR + 256;          // 1 + 4*STAGES + 3*TILES mbarriers + the TMEM base slot
+    // side region (fp32): q of the side row (pre-scaled) [HD], one block of its p [BKV], the lone tail key's k [HD], v [HD]
+    static constexpr int SMEM_BYTES = OFF_SIDE + (3 * HD + BKV) * 4;
     // TMEM columns per query tile: S block at +0 (64 fp32 cols) -- overwritten in place by P (bf16 pairs, 32 cols) once
     // the softmax has pulled S into registers -- and the O accumulator (HD fp32 cols) at +64.
     static constexpr uint32_t TM_O = 64;
@@ -65,12 +76,14 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
 
 template <int HD>
 __global__ void __launch_bounds__(THREADS, Geo<HD>::MIN_CTAS)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                     const __grid_constant__ CUtensorMap tm_tail, __nv_bfloat16* __restrict__ out, int S, int D,
-                     int tail_rows, float scale_log2) {
+                     const __grid_constant__ CUtensorMap tm_tail, const __nv_bfloat16* __restrict__ qkv,
+                     __nv_bfloat16* __restrict__ out, int S, int D, int tail_rows, float scale_log2, int side_row) {
     using G = Geo<HD>;
     constexpr int ATOMS = G::ATOMS, Q_ATOM = G::Q_ATOM, KV_ATOM = G::KV_ATOM, Q_BYTES = G::Q_BYTES,
                   KV_BYTES = G::KV_BYTES, OFF_Q = G::OFF_Q, OFF_K = G::OFF_K, OFF_V = G::OFF_V, OFF_BAR = G::OFF_BAR;
@@ -86,7 +99,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint64_t* s_full = v_empty + STAGES;     // [TILES] S_j in TMEM (also: every earlier MMA, incl. this tile's P V, done)
     uint64_t* p_full = s_full + TILES;       // [TILES] S_j consumed, P_j written to TMEM, O rescaled if needed (1 arrival/warp)
     uint64_t* o_done = p_full + TILES;       // [TILES] last P V accumulated
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + TILES);
+    uint64_t* kt_full = o_done + TILES;      // the lone tail key's k / v rows are in shared memory (fp32)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kt_full + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -96,7 +110,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int row_base = frame * S;          // first token row of this frame in the [M, 3D] matrix
     const int n_full = S / BKV;              // full KV blocks
     const int tail_valid = S - n_full * BKV; // valid keys in the tail block (0 = no tail)
-    const int n_blocks = n_full + (tail_valid > 0 ? 1 : 0);
+    const bool tail_epi = tail_valid == 1 && n_full >= 1;  // lone tail key: folded in by the epilogues, no KV block
+    const int n_blocks = n_full + ((tail_valid > 0 && !tail_epi) ? 1 : 0);
     const int n_tiles = (q0 + BQ < S) ? TILES : 1;  // tiles of this CTA that hold at least one query row
 
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
@@ -122,6 +137,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 mbar_init(&p_full[t], 4);
                 mbar_init(&o_done[t], 1);
             }
+            mbar_init(kt_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -134,8 +150,94 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == SOFTMAX_WARPS) {
-        // ------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------ TMA producer (+ the side row, see header)
         {
+            constexpr int DPL = HD / 32;  // output dims per lane of the side row
+            const bool side = side_row != 0 && blockIdx.x == 0;
+            float* q_side = reinterpret_cast<float*>(smem + G::OFF_SIDE);  // [HD] q * scale * log2e
+            float* p_side = q_side + HD;                                   // [BKV] probabilities of the current block
+            float* kt_side = p_side + BKV;                                 // [HD] k of the lone tail key
+            float* vt_side = kt_side + HD;                                 // [HD] v of the lone tail key
+            if (tail_epi) {
+                const __nv_bfloat16* kg = qkv + static_cast<size_t>(row_base + S - 1) * (3 * D) + D + head * HD;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) {
+                    kt_side[lane * DPL + i] = __bfloat162float(kg[lane * DPL + i]);
+                    vt_side[lane * DPL + i] = __bfloat162float(kg[D + lane * DPL + i]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(kt_full);
+            }
+            float m_run = -INFINITY, l_lane = 0.f, o_acc[DPL];
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) o_acc[i] = 0.f;
+            if (side) {
+                const __nv_bfloat16* qg = qkv + static_cast<size_t>(row_base + S - 1) * (3 * D) + head * HD;
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) q_side[lane * DPL + i] = __bfloat162float(qg[lane * DPL + i]) * scale_log2;
+                __syncwarp();
+            }
+            // One 64-key block of the side row: scores on lanes (keys lane, lane+32), online softmax across the warp,
+            // then every lane accumulates its DPL output dims over the block's keys.
+            auto side_block = [&](int jj) {
+                const int st = jj % STAGES;
+                const uint32_t ph = (jj / STAGES) & 1;
+                const bool tail = jj >= n_full;
+                const int rows = tail ? tail_rows : BKV;
+                const int atom_stride = tail ? tail_rows * 128 : KV_ATOM;
+                mbar_wait(&k_full[st], ph);
+                const uint8_t* kb = smem + OFF_K + st * KV_BYTES;
+                float sc[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int key = lane + 32 * h;
+                    float a0 = 0.f, a1 = 0.f;
+                    if (key < rows) {
+#pragma unroll
+                        for (int a = 0; a < ATOMS; ++a)
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const uint4 kk = *reinterpret_cast<const uint4*>(kb + a * atom_stride + key * 128 + ((c ^ (key & 7)) << 4));
+                                const float4 qa = *reinterpret_cast<const float4*>(q_side + a * 64 + c * 8);
+                                const float4 qb = *reinterpret_cast<const float4*>(q_side + a * 64 + c * 8 + 4);
+                                a0 = fmaf(bf_lo(kk.x), qa.x, a0); a1 = fmaf(bf_hi(kk.x), qa.y, a1);
+                                a0 = fmaf(bf_lo(kk.y), qa.z, a0); a1 = fmaf(bf_hi(kk.y), qa.w, a1);
+                                a0 = fmaf(bf_lo(kk.z), qb.x, a0); a1 = fmaf(bf_hi(kk.z), qb.y, a1);
+                                a0 = fmaf(bf_lo(kk.w), qb.z, a0); a1 = fmaf(bf_hi(kk.w), qb.w, a1);
+                            }
+                    }
+                    sc[h] = (key < rows && jj * BKV + key < S) ? a0 + a1 : -INFINITY;
+                }
+                float mb = fmaxf(sc[0], sc[1]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+                const float m_new = fmaxf(m_run, mb);  // finite: every block holds at least one valid key
+                const float corr = ex2(m_run - m_new);
+                const float p0 = ex2(sc[0] - m_new), p1 = ex2(sc[1] - m_new);
+                l_lane = fmaf(l_lane, corr, p0 + p1);
+                m_run = m_new;
+                p_side[lane] = p0;
+                p_side[lane + 32] = p1;
+                __syncwarp();
+                mbar_wait(&v_full[st], ph);
+                const uint8_t* vb = smem + OFF_V + st * KV_BYTES + ((lane * DPL) >> 6) * atom_stride;
+                const int boff = ((lane * DPL) & 63) * 2;  // byte offset of this lane's dims inside the 128-byte row
+#pragma unroll
+                for (int i = 0; i < DPL; ++i) o_acc[i] *= corr;
+#pragma unroll 4
+                for (int key = 0; key < rows; ++key) {
+                    const float pk = p_side[key];
+                    const uint8_t* vr = vb + key * 128 + ((((boff >> 4) ^ (key & 7)) << 4) | (boff & 15));
+#pragma unroll
+                    for (int i = 0; i < DPL; i += 2) {
+                        const uint32_t vv = *reinterpret_cast<const uint32_t*>(vr + 2 * i);
+                        o_acc[i] = fmaf(pk, bf_lo(vv), o_acc[i]);
+                        o_acc[i + 1] = fmaf(pk, bf_hi(vv), o_acc[i + 1]);
+                    }
+                }
+                __syncwarp();  // p_side is rewritten by the next block
+            };
+
             if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, n_tiles * Q_BYTES);
                 for (int t = 0; t < n_tiles; ++t)
@@ -168,6 +270,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                                     2 * D + head * HD + a * 64, r);
                 }
                 __syncwarp();
+                // the side row trails the loads by one block; its stage is only refilled STAGES-1 iterations from now
+                if (side && j > 0) side_block(j - 1);
+            }
+            if (side) {
+                side_block(n_blocks - 1);
+                float l = l_lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+                if (tail_epi) {  // the lone tail key: one more online-softmax step, dims spread over the lanes
+                    float st = 0.f;
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) st = fmaf(q_side[lane * DPL + i], kt_side[lane * DPL + i], st);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) st += __shfl_xor_sync(0xffffffffu, st, o);
+                    const float m_new = fmaxf(m_run, st);
+                    const float corr = ex2(m_run - m_new), pt = ex2(st - m_new);
+                    l = fmaf(l, corr, pt);
+#pragma unroll
+                    for (int i = 0; i < DPL; ++i) o_acc[i] = fmaf(o_acc[i], corr, pt * vt_side[lane * DPL + i]);
+                }
+                const float inv = 1.0f / l;
+                __nv_bfloat16* o = out + static_cast<size_t>(row_base + S - 1) * D + head * HD + lane * DPL;
+#pragma unroll
+                for (int i = 0; i < DPL; i += 2)
+                    *reinterpret_cast<uint32_t*>(o + i) = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
             }
         }
     } else if (warp == SOFTMAX_WARPS + 1) {
@@ -366,11 +493,39 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 if (lane == 0) mbar_arrive(&p_full[t]);  // one arrival per softmax warp
             }
 
+            // The lone tail key (see header): s_t = q_row . k_t from this row's Q tile line in shared memory, then an exact
+            // reference update. Computed before the o_done wait: it only needs Q and the side region.
+            float alpha = 1.f, p_t = 0.f;
+            const float* vt_side = reinterpret_cast<const float*>(smem + G::OFF_SIDE) + 2 * HD + BKV;
+            if (tail_epi && warp_live) {
+                const float* kt_side = vt_side - HD;
+                mbar_wait(kt_full, 0);
+                const uint8_t* qrow = smem + OFF_Q + t * Q_BYTES + r * 128;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 qq = *reinterpret_cast<const uint4*>(qrow + a * Q_ATOM + ((c ^ (r & 7)) << 4));
+                        const float4 ka = *reinterpret_cast<const float4*>(kt_side + a * 64 + c * 8);
+                        const float4 kb = *reinterpret_cast<const float4*>(kt_side + a * 64 + c * 8 + 4);
+                        a0 = fmaf(bf_lo(qq.x), ka.x, a0); a1 = fmaf(bf_hi(qq.x), ka.y, a1);
+                        a0 = fmaf(bf_lo(qq.y), ka.z, a0); a1 = fmaf(bf_hi(qq.y), ka.w, a1);
+                        a0 = fmaf(bf_lo(qq.z), kb.x, a0); a1 = fmaf(bf_hi(qq.z), kb.y, a1);
+                        a0 = fmaf(bf_lo(qq.w), kb.z, a0); a1 = fmaf(bf_hi(qq.w), kb.w, a1);
+                    }
+                const float s_t = (a0 + a1) * scale_log2;
+                const float new_ref = fmaxf(m_ref, s_t);
+                alpha = ex2(m_ref - new_ref);
+                p_t = ex2(s_t - new_ref);
+                l_run = fmaf(l_run, alpha, p_t);
+            }
             mbar_wait(&o_done[t], 0);
             tc_fence_after();
             const int q = tile_q0 + r;
             if (warp_live) {
                 const float inv = 1.0f / l_run;
+                const float ai = alpha * inv, pi = p_t * inv;
                 __nv_bfloat16* o = out + static_cast<size_t>(row_base + q) * D + head * HD;
 #pragma unroll
                 for (int c = 0; c < HD; c += 32) {
@@ -380,11 +535,27 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     if (q < S) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 8) {
+                            float y[8];
+                            if (tail_epi) {
+                                const float4 va = *reinterpret_cast<const float4*>(vt_side + c + i);
+                                const float4 vb = *reinterpret_cast<const float4*>(vt_side + c + i + 4);
+                                y[0] = fmaf(__uint_as_float(v[i + 0]), ai, pi * va.x);
+                                y[1] = fmaf(__uint_as_float(v[i + 1]), ai, pi * va.y);
+                                y[2] = fmaf(__uint_as_float(v[i + 2]), ai, pi * va.z);
+                                y[3] = fmaf(__uint_as_float(v[i + 3]), ai, pi * va.w);
+                                y[4] = fmaf(__uint_as_float(v[i + 4]), ai, pi * vb.x);
+                                y[5] = fmaf(__uint_as_float(v[i + 5]), ai, pi * vb.y);
+                                y[6] = fmaf(__uint_as_float(v[i + 6]), ai, pi * vb.z);
+                                y[7] = fmaf(__uint_as_float(v[i + 7]), ai, pi * vb.w);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[i + e]) * inv;
+                            }
                             uint4 w;
-                            w.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv, __uint_as_float(v[i + 1]) * inv);
-                            w.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-                            w.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-                            w.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+                            w.x = pack_bf16x2(y[0], y[1]);
+                            w.y = pack_bf16x2(y[2], y[3]);
+                            w.z = pack_bf16x2(y[4], y[5]);
+                            w.w = pack_bf16x2(y[6], y[7]);
                             *reinterpret_cast<uint4*>(o + c + i) = w;
                         }
                     }
@@ -403,8 +574,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 template <int HD>
 cudaError_t launch_attention_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
-                                __nv_bfloat16* out, int frames, int S, int heads, float softmax_scale,
-                                cudaStream_t stream) {
+                                const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads,
+                                float softmax_scale, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -412,10 +583,12 @@ cudaError_t launch_attention_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_k
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid((S + BQ * TILES - 1) / (BQ * TILES), heads, frames);
+    // side-row mode: S = k * 256 + 1 (k >= 1) -- the leftover query row rides on the producer warp of CTA 0
+    const int side_row = (S > BQ * TILES && S % (BQ * TILES) == 1 && qkv != nullptr) ? 1 : 0;
+    dim3 grid(side_row ? S / (BQ * TILES) : (S + BQ * TILES - 1) / (BQ * TILES), heads, frames);
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    attention_fwd_kernel<HD><<<grid, THREADS, Geo<HD>::SMEM_BYTES, stream>>>(tm_q, tm_kv, tm_tail, out, S, heads * HD,
-                                                                             attention_tail_rows(S), scale_log2);
+    attention_fwd_kernel<HD><<<grid, THREADS, Geo<HD>::SMEM_BYTES, stream>>>(
+        tm_q, tm_kv, tm_tail, qkv, out, S, heads * HD, attention_tail_rows(S), scale_log2, side_row);
     return cudaGetLastError();
 }
 
@@ -429,12 +602,12 @@ int attention_tail_rows(int S) {
 }
 
 cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
-                             __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
-                             cudaStream_t stream) {
+                             const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads, int head_dim,
+                             float softmax_scale, cudaStream_t stream) {
     if (frames <= 0 || S <= 0 || heads <= 0) return cudaErrorInvalidValue;
     if (S % BKV > 32) return cudaErrorInvalidValue;  // ragged tail of at most 32 keys (1025 % 64 == 1)
-    if (head_dim == 64) return launch_attention_hd<64>(tm_q, tm_kv, tm_tail, out, frames, S, heads, softmax_scale, stream);
-    if (head_dim == 128) return launch_attention_hd<128>(tm_q, tm_kv, tm_tail, out, frames, S, heads, softmax_scale, stream);
+    if (head_dim == 64) return launch_attention_hd<64>(tm_q, tm_kv, tm_tail, qkv, out, frames, S, heads, softmax_scale, stream);
+    if (head_dim == 128) return launch_attention_hd<128>(tm_q, tm_kv, tm_tail, qkv, out, frames, S, heads, softmax_scale, stream);
     return cudaErrorInvalidValue;
 }
 

@@ -58,9 +58,10 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 int attention_q_rows();
 int attention_kv_rows();
 int attention_tail_rows(int S);
+// qkv: base of the [frames*S, 3*heads*head_dim] matrix the three maps describe (the side query row is read directly).
 cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
-                             __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
-                             cudaStream_t stream);
+                             const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads, int head_dim,
+                             float softmax_scale, cudaStream_t stream);
 
 // ---- row-wise / bandwidth kernels --------------------------------------------------------------------------------
 // y[r,:] = LN(x[r,:]) * w + b (b may be null -> RMSNorm when rms != 0). x fp32 [rows, D] -> y bf16 [rows, D].

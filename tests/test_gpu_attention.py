@@ -16,7 +16,7 @@ def _attn_ref(qkv, frames, S, H, d):
 
 
 @pytest.mark.parametrize("frames,S,H,d", [(1, 128, 1, 64), (1, 256, 2, 64), (2, 1025, 2, 64), (3, 130, 4, 64),
-                                          (1, 1025, 16, 64), (2, 95, 1, 64),
+                                          (1, 1025, 16, 64), (2, 95, 1, 64), (3, 257, 2, 64), (2, 513, 3, 64), (2, 257, 2, 128),
                                           (1, 128, 1, 128), (2, 1025, 2, 128), (1, 1025, 25, 128), (2, 95, 3, 128)])
 def test_attention_matches_reference(frames, S, H, d):
     g = torch.Generator().manual_seed(S + H + d)
