@@ -59,19 +59,19 @@ struct Cfg {
 template <bool kGelu>
 __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep, float mean, float rstd) {
     if (ep.ln_stats) {
-        if (ep.ln_wsum) {
+        // x = rstd * (acc - mean * wsum) + bias as two FMAs per element: fma(rstd, acc, fma(-mean*rstd, wsum, bias))
+        const float nmr = -mean * rstd;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 32; j += 4) {
+            float4 b = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.ln_wsum) {
                 const float4 w = __ldg(reinterpret_cast<const float4*>(ep.ln_wsum + col0 + j));
-                x[j] = rstd * fmaf(-mean, w.x, x[j]); x[j + 1] = rstd * fmaf(-mean, w.y, x[j + 1]);
-                x[j + 2] = rstd * fmaf(-mean, w.z, x[j + 2]); x[j + 3] = rstd * fmaf(-mean, w.w, x[j + 3]);
+                b.x = fmaf(nmr, w.x, b.x); b.y = fmaf(nmr, w.y, b.y); b.z = fmaf(nmr, w.z, b.z); b.w = fmaf(nmr, w.w, b.w);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] *= rstd;
+            x[j] = fmaf(rstd, x[j], b.x); x[j + 1] = fmaf(rstd, x[j + 1], b.y);
+            x[j + 2] = fmaf(rstd, x[j + 2], b.z); x[j + 3] = fmaf(rstd, x[j + 3], b.w);
         }
-    }
-    if (ep.bias) {
+    } else if (ep.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
