@@ -599,7 +599,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
     };
     auto residual_producer = [&](GemmEpilogue& ep) {
         ep.out_f32 = 1;
-        if (fused) { ep.fused_residual = 1; ep.stats_out = h->stats; }
+        if (fused) { ep.fused_residual = 1; ep.resid_in = h->x; ep.stats_out = h->stats; }
         else ep.accumulate = 1;
     };
 
@@ -856,7 +856,7 @@ int aigv_gemm_residual_stats(const void* a_bf16, const void* w_bf16, const float
     if (make_tmap_2d(&tc, x_f32, 1, M, N, N, gemm_box_rows_c(), gemm_box_cols_c(true))) return AIGV_ERR_INVALID;
     if (make_tmap_2d(&tx, xb_bf16, 0, M, N, N, gemm_box_rows_c(), gemm_box_cols_c(false))) return AIGV_ERR_INVALID;
     GemmEpilogue ep;
-    ep.bias = bias; ep.colscale = colscale; ep.out_f32 = 1; ep.fused_residual = 1;
+    ep.bias = bias; ep.colscale = colscale; ep.out_f32 = 1; ep.fused_residual = 1; ep.resid_in = x_f32;
     ep.stats_out = reinterpret_cast<float2*>(stats);
     AIGV_TRY0(launch_gemm(ta, tb, tc, M, N, K, ep, device_num_sms(), static_cast<cudaStream_t>(stream), &tx));
     return AIGV_OK;

@@ -37,16 +37,19 @@ constexpr int STG_BYTES = 4096;
 constexpr uint32_t TMEM_COLS = 512;
 
 // Shapes of the same kernel: the GELU epilogue is instruction-issue heavy and wants 16 epilogue warps (4 per SMSP) at the
-// price of one pipeline stage; the plain epilogues keep 8 warps and 6 stages; the fused-residual epilogue (kResid) needs
+// price of one pipeline stage; the plain epilogues keep 8 warps and 6 stages; the fused-residual epilogue comes in two
+// forms: kResid == 2 (long K, fc2: the mainloop hides a serial epilogue) re-uses ONE staging tile per warp for the x_old
+// fetch, the fp32 x_new store and the bf16 copy and keeps 6 stages (measured: 4 instead of 6 stages costs 8% on fc2);
+// kResid == 1 (short K, proj: the epilogue is the critical path) needs
 // three staging tiles per warp (two fp32 tiles for the x_old prefetch / x_new store, one bf16 tile) and runs 4 stages.
-template <int kEpiWarps, bool kResid>
+template <int kEpiWarps, int kResid>
 struct Cfg {
     static constexpr int EPI_WARPS = kEpiWarps;          // multiple of 4: warp%4 = TMEM lane quadrant
     static constexpr int SLICES = kEpiWarps / 4;         // column slices of the 256-column tile
     static constexpr int SLICE_COLS = BN / SLICES;       // 64 or 128 columns per warp
-    static constexpr int STAGES = kResid ? 4 : (kEpiWarps == 16 ? 5 : 6);
+    static constexpr int STAGES = kResid == 1 ? 4 : (kEpiWarps == 16 ? 5 : 6);
     static constexpr int THREADS = (kEpiWarps + 2) * 32;
-    static constexpr int WARP_STG = kResid ? 3 * STG_BYTES : STG_BYTES;
+    static constexpr int WARP_STG = kResid == 1 ? 3 * STG_BYTES : STG_BYTES;
     static constexpr int OFF_STG = STAGES * STAGE_BYTES;
     static constexpr int OFF_BAR = OFF_STG + kEpiWarps * WARP_STG;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;     // 2*STAGES + 4 pipeline barriers, 2 per epilogue warp, TMEM slot
@@ -91,7 +94,7 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
     }
 }
 
-template <bool kGelu, bool kOutF32, int kEpiWarps, bool kResid>
+template <bool kGelu, bool kOutF32, int kEpiWarps, int kResid>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<kEpiWarps, kResid>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
@@ -223,20 +226,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // kResid: x_old does not depend on the MMAs: start fetching this warp's first staging tile before waiting
             auto issue_xload = [&](int c) {
                 if (lane == 0 && row0 < M && colb + c < N) {
-                    uint64_t* bar = &xload_bar[2 * warp + ((c >> 5) & 1)];
+                    const int buf = kResid == 2 ? 0 : (c >> 5) & 1;  // the serial form has a single staging tile
+                    uint64_t* bar = &xload_bar[2 * warp + buf];
                     mbar_arrive_expect_tx(bar, STG_BYTES);
-                    tma_load_2d(stg + ((c >> 5) & 1) * STG_BYTES, &tmC, bar, colb + c, row0);
+                    tma_load_2d(stg + buf * STG_BYTES, &tmC, bar, colb + c, row0);
                 }
             };
             if (kResid) {
                 if (lane == 0) tma_store_wait_read<0>();  // staging tiles of the previous output tile have been read out
                 __syncwarp();
                 issue_xload(0);
+                if (kResid == 2 && row0 + lane < M && colb < N)  // the later chunks are fetched serially: have them in L2
+                    prefetch_l2_bulk(ep.resid_in + static_cast<size_t>(row0 + lane) * N + colb,
+                                     4u * static_cast<uint32_t>(N - colb < SLICE_COLS ? N - colb : SLICE_COLS));
             }
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * SLICE_COLS;
-            // LayerNorm-fused consumer: this thread's row statistics
+            // LayerNorm-fused consumer: this thread's row statistics (fetched ahead of the accumulator wait)
             float mean = 0.f, rstd = 1.f;
             if (ep.ln_stats) {
                 const int row = row0 + lane;
@@ -250,6 +254,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mean = ep.ln_wsum ? sx * ep.ln_inv_d : 0.f;
                 rstd = rsqrtf(fmaxf(sq * ep.ln_inv_d - mean * mean, 0.f) + ep.ln_eps);
             }
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + slice * SLICE_COLS;
             // 32 accumulator columns -> (LN) / bias / GELU / scale in fp32 (in place). The accumulator stage is handed
             // back to the MMA warp as soon as this warp's LAST tcgen05.ld of the tile has completed.
             auto load32 = [&](int c, float (&x)[32]) {
@@ -279,7 +286,60 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tma_store_commit();
                 }
             };
-            if (kResid) {
+            if (kResid == 2) {
+                // Fused residual producer, serial form: one staging tile per warp. Per 32-column chunk: x_old (TMA) ->
+                // in-place x_new -> fp32 store -> (every second chunk) the 64-column bf16 copy through the same tile ->
+                // fetch of the next chunk. Every step waits for the previous one; the long mainloop hides it.
+                float rs = 0.f, rq = 0.f;
+                uint32_t pbr[32];  // bf16 pairs of the current 64-column pair of chunks
+                uint8_t* frow = stg + lane * 128;
+#pragma unroll
+                for (int c = 0; c < SLICE_COLS; c += 32) {
+                    const int b = (c >> 5) & 1;
+                    float x[32];
+                    load32(c, x);
+                    if (!(row0 < M && colb + c < N)) continue;  // warp-uniform: nothing of this chunk is inside C
+                    mbar_wait(&xload_bar[2 * warp], xphase & 1);
+                    xphase ^= 1u;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4* slot = reinterpret_cast<uint4*>(frow + ((j ^ sw) << 4));
+                        const uint4 o = *slot;
+                        const float y0 = __uint_as_float(o.x) + x[4 * j], y1 = __uint_as_float(o.y) + x[4 * j + 1];
+                        const float y2 = __uint_as_float(o.z) + x[4 * j + 2], y3 = __uint_as_float(o.w) + x[4 * j + 3];
+                        rs += (y0 + y1) + (y2 + y3);
+                        rq += (y0 * y0 + y1 * y1) + (y2 * y2 + y3 * y3);
+                        *slot = make_uint4(__float_as_uint(y0), __float_as_uint(y1), __float_as_uint(y2), __float_as_uint(y3));
+                        pbr[16 * b + 2 * j] = pack_bf16x2(y0, y1);
+                        pbr[16 * b + 2 * j + 1] = pack_bf16x2(y2, y3);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, stg, colb + c, row0);  // x_new, fp32
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                    }
+                    __syncwarp();
+                    if (b) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<uint4*>(frow + ((q ^ sw) << 4)) =
+                                make_uint4(pbr[4 * q], pbr[4 * q + 1], pbr[4 * q + 2], pbr[4 * q + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmX, stg, colb + c - 32, row0);  // x_new, bf16 (64 columns)
+                            tma_store_commit();
+                            tma_store_wait_read<0>();
+                        }
+                        __syncwarp();
+                    }
+                    if (c + 32 < SLICE_COLS) issue_xload(c + 32);
+                }
+                if (ep.stats_out && row0 + lane < M && colb < N)
+                    ep.stats_out[static_cast<size_t>(colb / SLICE_COLS) * M + row0 + lane] = make_float2(rs, rq);
+            } else if (kResid) {
                 // Fused residual producer: x_new = x_old + colscale * (acc + bias) computed here (x_old tiles arrive by
                 // TMA, double buffered), written back as fp32 (the residual stream) AND as bf16 (the next GEMM's A
                 // operand), with the row's (sum, sum of squares) accumulated for the LayerNorm the next GEMM applies.
@@ -370,7 +430,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <bool kGelu, bool kOutF32, int kEpiWarps, bool kResid>
+template <bool kGelu, bool kOutF32, int kEpiWarps, int kResid>
 cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmX,
                            int M, int N, int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
     using C = Cfg<kEpiWarps, kResid>;
@@ -404,16 +464,18 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     if (ep.fused_residual) {
         // x_new = x_old + colscale*(acc+bias) in the SM; needs the bf16 copy map and 64-column-aligned N
         if (!ep.out_f32 || ep.gelu || ep.accumulate || !tmX || (N % 64) != 0) return cudaErrorInvalidValue;
-        return launch_variant<false, true, 8, true>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
+        // long K: the mainloop hides a serial single-buffer epilogue and keeps all 6 stages; short K: pipelined, 4 stages
+        if (K >= 2048) return launch_variant<false, true, 8, 2>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
+        return launch_variant<false, true, 8, 1>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
     }
     // The GELU epilogue is instruction-issue heavy: 16 epilogue warps and 5 stages; everything else 8 warps and 6 stages
     // (measured: the fp32 reduce-add epilogue of proj does not gain from more warps: 948 vs 1016 TFLOP/s).
     if (ep.gelu) {
-        return ep.out_f32 ? launch_variant<true, true, 16, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream)
-                          : launch_variant<true, false, 16, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+        return ep.out_f32 ? launch_variant<true, true, 16, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream)
+                          : launch_variant<true, false, 16, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
     }
-    if (ep.out_f32) return launch_variant<false, true, 8, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
-    return launch_variant<false, false, 8, false>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    if (ep.out_f32) return launch_variant<false, true, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    return launch_variant<false, false, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
 }
 
 }  // namespace aigv

@@ -26,6 +26,7 @@ struct GemmEpilogue {
     // tiles arrive by TMA), stored back as fp32 AND as bf16 through the extra map, and (sum, sum of squares) of every
     // row of C_new are written to stats_out[slice][M], one slice per gemm_stats_slice_cols() columns of C.
     int fused_residual = 0;
+    const float* resid_in = nullptr;  // == the C matrix (row stride N): lets the epilogue prefetch its rows into L2
     float2* stats_out = nullptr;
 };
 
