@@ -616,8 +616,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
                                              h->num_sms, st), "qkv gemm");
         }
         if (h->cfg.qk_normalization) {
-            AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st), "q_norm");
-            AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.knw, M, D, 3 * D, D, eps, st), "k_norm");
+            AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st, w.knw, D), "q_norm+k_norm");
         }
         AIGV_LAUNCH(K_ATTENTION, launch_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->qkv, h->attn, n, S, h->H, h->hd, scale, st),
                  "attention");

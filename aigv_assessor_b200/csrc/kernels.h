@@ -69,8 +69,9 @@ cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, 
 cudaError_t launch_norm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows, int D,
                                     float eps, int rms, cudaStream_t stream);
 // In-place RMSNorm over column block [col0, col0+D) of a bf16 matrix with row stride ld (q/k norm of InternViT-6B).
+// With w1: a second column block [col1, col1+D) with its own weight in the same launch (q_norm + k_norm).
 cudaError_t launch_rmsnorm_bf16_inplace(__nv_bfloat16* x, const float* w, int rows, int D, int ld, int col0, float eps,
-                                        cudaStream_t stream);
+                                        cudaStream_t stream, const float* w1 = nullptr, int col1 = 0);
 // pixel_values bf16 [n,3,S,S] -> patches bf16 [n*g*g, Kpad] with (c,ky,kx) flattening, zero padded to Kpad.
 cudaError_t launch_im2col(const __nv_bfloat16* pv, __nv_bfloat16* patches, int n, int img, int patch, int kpad,
                           cudaStream_t stream);

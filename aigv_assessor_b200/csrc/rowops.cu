@@ -142,62 +142,94 @@ norm_f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w
     }
 }
 
+// In-place RMSNorm of up to two column blocks of a bf16 matrix in one launch (blockIdx.y selects the block: q_norm and
+// k_norm of InternViT-6B act on adjacent column blocks of the qkv matrix). kRegChunks > 0: the row block is held in
+// registers (kRegChunks x 16 bytes per lane), so it is read from memory once; 0: two passes for any width.
+template <int kRegChunks>
 __global__ void __launch_bounds__(256)
-rmsnorm_bf16_inplace_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ w, int rows, int D, int ld,
-                            int col0, float eps) {
+rmsnorm_bf16_inplace_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ w0, const float* __restrict__ w1,
+                            int rows, int D, int ld, int col0, int col1, float eps) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    __nv_bfloat16* xr = x + static_cast<size_t>(row) * ld + col0;
+    const float* __restrict__ w = blockIdx.y ? w1 : w0;
+    __nv_bfloat16* xr = x + static_cast<size_t>(row) * ld + (blockIdx.y ? col1 : col0);
     float q = 0.f;
-    for (int i = lane * 8; i < D; i += 256) {
-        const uint4 t = *reinterpret_cast<const uint4*>(xr + i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    uint4 buf[kRegChunks > 0 ? kRegChunks : 1];
+    if (kRegChunks > 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = __bfloat1622float2(h[k]);
-            q += f.x * f.x + f.y * f.y;
+        for (int c = 0; c < kRegChunks; ++c) {
+            const int i = lane * 8 + c * 256;
+            buf[c] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < D) buf[c] = *reinterpret_cast<const uint4*>(xr + i);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&buf[c]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h[k]);
+                q += f.x * f.x + f.y * f.y;
+            }
+        }
+    } else {
+        for (int i = lane * 8; i < D; i += 256) {
+            const uint4 t = *reinterpret_cast<const uint4*>(xr + i);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __bfloat1622float2(h[k]);
+                q += f.x * f.x + f.y * f.y;
+            }
         }
     }
     const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
-    for (int i = lane * 8; i < D; i += 256) {
-        uint4 t = *reinterpret_cast<const uint4*>(xr + i);
+    // InternRMSNorm: weight * (x * rstd)  (modeling_intern_vit.py:39-43), one rounding at the store
+    auto scale_store = [&](uint4 t, int i) {
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w + i)), wb = __ldg(reinterpret_cast<const float4*>(w + i + 4));
+        const float ws[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float2 f = __bfloat1622float2(h[k]);
-            // InternRMSNorm: weight * (x * rstd)  (modeling_intern_vit.py:39-43), one rounding at the store
-            const float a = f.x * rstd * w[i + 2 * k];
-            const float c = f.y * rstd * w[i + 2 * k + 1];
-            h[k] = __floats2bfloat162_rn(a, c);
+            h[k] = __floats2bfloat162_rn(f.x * rstd * ws[2 * k], f.y * rstd * ws[2 * k + 1]);
         }
         *reinterpret_cast<uint4*>(xr + i) = t;
+    };
+    if (kRegChunks > 0) {
+#pragma unroll
+        for (int c = 0; c < kRegChunks; ++c) {
+            const int i = lane * 8 + c * 256;
+            if (i < D) scale_store(buf[c], i);
+        }
+    } else {
+        for (int i = lane * 8; i < D; i += 256) scale_store(*reinterpret_cast<const uint4*>(xr + i), i);
     }
 }
 
+// One thread per (patch, channel, ky) strip of `patch` pixels (28 contiguous bytes at patch 14), plus one thread per patch
+// for the zero padding up to kpad: no per-element index arithmetic, destination rows written contiguously.
 __global__ void __launch_bounds__(256)
 im2col_kernel(const __nv_bfloat16* __restrict__ pv, __nv_bfloat16* __restrict__ patches, int n, int img, int patch,
               int kpad) {
     const int g = img / patch;
-    const int kp2 = kpad >> 1;
+    const int strips = 3 * patch + 1;  // + the padding strip
     const int kreal = 3 * patch * patch;
-    const size_t total = static_cast<size_t>(n) * g * g * kp2;
+    const size_t total = static_cast<size_t>(n) * g * g * strips;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int k = static_cast<int>(idx % kp2) * 2;
-        const size_t prow = idx / kp2;
-        uint32_t v = 0;
-        if (k < kreal) {
-            const int p = static_cast<int>(prow % (g * g));
-            const int f = static_cast<int>(prow / (g * g));
-            const int py = p / g, px = p % g;
-            const int c = k / (patch * patch);
-            const int rem = k - c * patch * patch;
-            const int ky = rem / patch, kx = rem % patch;
-            const size_t src = ((static_cast<size_t>(f) * 3 + c) * img + (py * patch + ky)) * img + px * patch + kx;
-            v = *reinterpret_cast<const uint32_t*>(pv + src);
+        const int s = static_cast<int>(idx % strips);
+        const size_t prow = idx / strips;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(patches + prow * kpad);
+        if (s == strips - 1) {
+            for (int k = kreal >> 1; k < (kpad >> 1); ++k) dst[k] = 0u;
+            continue;
         }
-        *reinterpret_cast<uint32_t*>(patches + prow * kpad + k) = v;
+        const int p = static_cast<int>(prow % (g * g));
+        const int f = static_cast<int>(prow / (g * g));
+        const int py = p / g, px = p - py * g;
+        const int c = s / patch, ky = s - c * patch;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(
+            pv + ((static_cast<size_t>(f) * 3 + c) * img + (py * patch + ky)) * img + px * patch);
+        dst += (s * patch) >> 1;
+        for (int k = 0; k < (patch >> 1); ++k) dst[k] = __ldg(src + k);
     }
 }
 
@@ -398,9 +430,17 @@ cudaError_t launch_norm_f32_to_bf16(const float* x, const float* w, const float*
 }
 
 cudaError_t launch_rmsnorm_bf16_inplace(__nv_bfloat16* x, const float* w, int rows, int D, int ld, int col0, float eps,
-                                        cudaStream_t stream) {
-    if (rows <= 0 || (D % 8) != 0 || (ld % 8) != 0 || (col0 % 8) != 0) return cudaErrorInvalidValue;
-    rmsnorm_bf16_inplace_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, w, rows, D, ld, col0, eps);
+                                        cudaStream_t stream, const float* w1, int col1) {
+    if (rows <= 0 || (D % 8) != 0 || (ld % 8) != 0 || (col0 % 8) != 0 || (col1 % 8) != 0) return cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (w1 && (reinterpret_cast<uintptr_t>(w1) & 15) != 0))
+        return cudaErrorInvalidValue;
+    const dim3 grid((rows + 7) / 8, w1 ? 2 : 1);
+    if (D <= 4 * 256)
+        rmsnorm_bf16_inplace_kernel<4><<<grid, 256, 0, stream>>>(x, w, w1, rows, D, ld, col0, col1, eps);
+    else if (D <= 13 * 256)
+        rmsnorm_bf16_inplace_kernel<13><<<grid, 256, 0, stream>>>(x, w, w1, rows, D, ld, col0, col1, eps);
+    else
+        rmsnorm_bf16_inplace_kernel<0><<<grid, 256, 0, stream>>>(x, w, w1, rows, D, ld, col0, col1, eps);
     return cudaGetLastError();
 }
 
@@ -408,7 +448,7 @@ cudaError_t launch_im2col(const __nv_bfloat16* pv, __nv_bfloat16* patches, int n
                           cudaStream_t stream) {
     if (n <= 0 || (patch % 2) != 0 || (kpad % 2) != 0 || kpad < 3 * patch * patch) return cudaErrorInvalidValue;
     const int g = img / patch;
-    const size_t total = static_cast<size_t>(n) * g * g * (kpad / 2);
+    const size_t total = static_cast<size_t>(n) * g * g * (3 * patch + 1);
     im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(pv, patches, n, img, patch, kpad);
     return cudaGetLastError();
 }

@@ -33,51 +33,57 @@ def from_bf16_bits(b: np.ndarray) -> np.ndarray:
     return (b.astype(np.uint32) << 16).view(np.float32)
 
 
-def make_weights(cfg: VisionPathConfig, seed: int = 0) -> dict[str, np.ndarray]:
-    rng = np.random.Generator(np.random.PCG64(seed))
+def weight_spec(cfg: VisionPathConfig):
+    """Yield (name, shape, dist) for every tensor of the path under the reference's state-dict names.
+
+    dist is ("uniform", fan_in) -- U(-1/sqrt(fan_in), 1/sqrt(fan_in)), torch's Linear/Conv default -- or
+    ("normal", std, mean). make_weights() draws them in this order; GPU-side generators (tools_bench_6b.py) reuse it.
+    """
     D, I, C, W = cfg.hidden_size, cfg.intermediate_size, cfg.llm_hidden, cfg.shuffled_width
     P = cfg.patch_size
-    sd: dict[str, np.ndarray] = {}
-
-    def uniform(shape, fan_in):
-        b = 1.0 / np.sqrt(fan_in)
-        return bf16_round(rng.uniform(-b, b, size=shape).astype(np.float32))
-
-    def normal(shape, std=1.0, mean=0.0):
-        return bf16_round((mean + std * rng.standard_normal(size=shape)).astype(np.float32))
-
     pre = "vision_model."
-    sd[pre + "embeddings.class_embedding"] = normal((1, 1, D))
-    sd[pre + "embeddings.position_embedding"] = normal((1, cfg.tokens, D))
-    sd[pre + "embeddings.patch_embedding.weight"] = uniform((D, 3, P, P), 3 * P * P)
-    sd[pre + "embeddings.patch_embedding.bias"] = uniform((D,), 3 * P * P)
+    yield pre + "embeddings.class_embedding", (1, 1, D), ("normal", 1.0, 0.0)
+    yield pre + "embeddings.position_embedding", (1, cfg.tokens, D), ("normal", 1.0, 0.0)
+    yield pre + "embeddings.patch_embedding.weight", (D, 3, P, P), ("uniform", 3 * P * P)
+    yield pre + "embeddings.patch_embedding.bias", (D,), ("uniform", 3 * P * P)
     for i in range(cfg.num_layers):
         lp = f"{pre}encoder.layers.{i}."
-        sd[lp + "ls1"] = normal((D,), 0.1 * cfg.initializer_factor, cfg.initializer_factor)
-        sd[lp + "ls2"] = normal((D,), 0.1 * cfg.initializer_factor, cfg.initializer_factor)
-        sd[lp + "attn.qkv.weight"] = uniform((3 * D, D), D)
+        yield lp + "ls1", (D,), ("normal", 0.1 * cfg.initializer_factor, cfg.initializer_factor)
+        yield lp + "ls2", (D,), ("normal", 0.1 * cfg.initializer_factor, cfg.initializer_factor)
+        yield lp + "attn.qkv.weight", (3 * D, D), ("uniform", D)
         if cfg.qkv_bias:
-            sd[lp + "attn.qkv.bias"] = uniform((3 * D,), D)
+            yield lp + "attn.qkv.bias", (3 * D,), ("uniform", D)
         if cfg.qk_normalization:
-            sd[lp + "attn.q_norm.weight"] = normal((D,), 0.1, 1.0)
-            sd[lp + "attn.k_norm.weight"] = normal((D,), 0.1, 1.0)
-        sd[lp + "attn.proj.weight"] = uniform((D, D), D)
-        sd[lp + "attn.proj.bias"] = uniform((D,), D)
-        sd[lp + "mlp.fc1.weight"] = uniform((I, D), D)
-        sd[lp + "mlp.fc1.bias"] = uniform((I,), D)
-        sd[lp + "mlp.fc2.weight"] = uniform((D, I), I)
-        sd[lp + "mlp.fc2.bias"] = uniform((D,), I)
-        sd[lp + "norm1.weight"] = normal((D,), 0.1, 1.0)
-        sd[lp + "norm2.weight"] = normal((D,), 0.1, 1.0)
+            yield lp + "attn.q_norm.weight", (D,), ("normal", 0.1, 1.0)
+            yield lp + "attn.k_norm.weight", (D,), ("normal", 0.1, 1.0)
+        yield lp + "attn.proj.weight", (D, D), ("uniform", D)
+        yield lp + "attn.proj.bias", (D,), ("uniform", D)
+        yield lp + "mlp.fc1.weight", (I, D), ("uniform", D)
+        yield lp + "mlp.fc1.bias", (I,), ("uniform", D)
+        yield lp + "mlp.fc2.weight", (D, I), ("uniform", I)
+        yield lp + "mlp.fc2.bias", (D,), ("uniform", I)
+        yield lp + "norm1.weight", (D,), ("normal", 0.1, 1.0)
+        yield lp + "norm2.weight", (D,), ("normal", 0.1, 1.0)
         if cfg.norm_type == "layer_norm":
-            sd[lp + "norm1.bias"] = normal((D,), 0.1)
-            sd[lp + "norm2.bias"] = normal((D,), 0.1)
-    sd["mlp1.0.weight"] = normal((W,), 0.1, 1.0)
-    sd["mlp1.0.bias"] = normal((W,), 0.1)
-    sd["mlp1.1.weight"] = uniform((C, W), W)
-    sd["mlp1.1.bias"] = uniform((C,), W)
-    sd["mlp1.3.weight"] = uniform((C, C), C)
-    sd["mlp1.3.bias"] = uniform((C,), C)
+            yield lp + "norm1.bias", (D,), ("normal", 0.1, 0.0)
+            yield lp + "norm2.bias", (D,), ("normal", 0.1, 0.0)
+    yield "mlp1.0.weight", (W,), ("normal", 0.1, 1.0)
+    yield "mlp1.0.bias", (W,), ("normal", 0.1, 0.0)
+    yield "mlp1.1.weight", (C, W), ("uniform", W)
+    yield "mlp1.1.bias", (C,), ("uniform", W)
+    yield "mlp1.3.weight", (C, C), ("uniform", C)
+    yield "mlp1.3.bias", (C,), ("uniform", C)
+
+
+def make_weights(cfg: VisionPathConfig, seed: int = 0) -> dict[str, np.ndarray]:
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: dict[str, np.ndarray] = {}
+    for name, shape, dist in weight_spec(cfg):
+        if dist[0] == "uniform":
+            b = 1.0 / np.sqrt(dist[1])
+            sd[name] = bf16_round(rng.uniform(-b, b, size=shape).astype(np.float32))
+        else:
+            sd[name] = bf16_round((dist[2] + dist[1] * rng.standard_normal(size=shape)).astype(np.float32))
     return sd
 
 

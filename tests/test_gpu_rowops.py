@@ -27,8 +27,8 @@ def test_norm(rows, D, rms):
     assert emax(got, ref) < 4e-3
 
 
-def test_rmsnorm_inplace_on_column_block():
-    rows, D = 200, 256
+@pytest.mark.parametrize("rows,D", [(200, 256), (77, 3200), (33, 4096)])  # register-resident (<=1024, <=3328) and two-pass
+def test_rmsnorm_inplace_on_column_block(rows, D):
     rng = np.random.default_rng(3)
     x = synth.bf16_round(rng.standard_normal((rows, 3 * D)).astype(np.float32))
     w = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
