@@ -83,7 +83,11 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
     }
     if (kGelu) {
 #pragma unroll
+#ifdef AIGV_GELU_AS7126  // the older Abramowitz-Stegun 7.1.26 form (18 issue slots per pair; fc1 2.4% slower)
         for (int j = 0; j < 32; j += 2) gelu_erf2(x[j], x[j + 1]);
+#else
+        for (int j = 0; j < 32; j += 2) gelu_sig2(x[j], x[j + 1]);
+#endif
     }
     if (ep.colscale) {
 #pragma unroll
@@ -471,8 +475,11 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     // The GELU epilogue is instruction-issue heavy: 16 epilogue warps and 5 stages; everything else 8 warps and 6 stages
     // (measured: the fp32 reduce-add epilogue of proj does not gain from more warps: 948 vs 1016 TFLOP/s).
     if (ep.gelu) {
-        return ep.out_f32 ? launch_variant<true, true, 16, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream)
-                          : launch_variant<true, false, 16, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+#ifndef AIGV_GELU_WARPS
+#define AIGV_GELU_WARPS 16
+#endif
+        return ep.out_f32 ? launch_variant<true, true, AIGV_GELU_WARPS, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream)
+                          : launch_variant<true, false, AIGV_GELU_WARPS, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
     }
     if (ep.out_f32) return launch_variant<false, true, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
     return launch_variant<false, false, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);

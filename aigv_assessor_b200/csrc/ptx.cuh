@@ -367,20 +367,29 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
     unpack2(fma2(mul2(ax, pack2(-1.0f, -1.0f)), q, pack2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), x0, x1);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float ax = fabsf(x);
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f)));
-    float p = 0.5f * 1.061405429f;
-    p = fmaf(p, t, 0.5f * -1.453152027f);
-    p = fmaf(p, t, 0.5f * 1.421413741f);
-    p = fmaf(p, t, 0.5f * -0.284496736f);
-    p = fmaf(p, t, 0.5f * 0.254829592f);
-    const float u = ax * 0.84932180028801907f;  // sqrt(log2(e) / 2): exp(-x^2/2) = 2^(-u^2)
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
-    const float q = (p * t) * e;
-    return fmaf(-ax, q, fmaxf(x, 0.0f));
+// Lighter erf GELU for the tensor-core epilogues: gelu(x) = x * Phi(x) with Phi(x) = 1 / (1 + 2^(x q(x^2))), where
+// x q(x^2) is the minimax fit of -2 log2(e) * atanh(erf(x / sqrt 2)) (cubic in x^2, argument clamped at |x| = 8 where
+// Phi is 0 / 1 in fp32): |gelu error| <= 5.5e-5 absolute for all x -- 70x below the bf16 rounding of an O(1) output --
+// with no cancellation for large negative x (2^(+big) -> inf -> rcp -> 0). Per pair: 6 packed FMA-pipe instructions,
+// 2 FMNMX, 4 MUFU (12 issue slots instead of 18 for gelu_erf2).
+__device__ __forceinline__ void gelu_sig2(float& x0, float& x1) {
+    const f32x2 x = pack2(x0, x1);
+    float u0, u1;
+    unpack2(mul2(x, x), u0, u1);
+    const f32x2 u = pack2(fminf(u0, 64.0f), fminf(u1, 64.0f));
+    f32x2 q = fma2(pack2(0.000911224284209311f, 0.000911224284209311f), u, pack2(-0.10617733001708984f, -0.10617733001708984f));
+    q = fma2(q, u, pack2(-2.301727056503296f, -2.301727056503296f));
+    float a0, a1;
+    unpack2(mul2(x, q), a0, a1);
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    float d0, d1;
+    unpack2(add2(pack2(e0, e1), pack2(1.0f, 1.0f)), d0, d1);
+    float r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    unpack2(mul2(x, pack2(r0, r1)), x0, x1);
 }
 
 }  // namespace aigv
