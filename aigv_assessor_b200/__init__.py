@@ -9,6 +9,9 @@ def __getattr__(name):  # torch-dependent pieces are imported lazily so config/s
     if name == "VisionEngine":
         from .engine import VisionEngine
         return VisionEngine
+    if name in ("metrics", "sharding", "tiling"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
     if name in ("install", "uninstall"):
         from . import plugin
         return getattr(plugin, name)
