@@ -323,7 +323,7 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
     h->stat_parts = (h->D + gemm_stats_slice_cols() - 1) / gemm_stats_slice_cols();
     {
         const char* e = getenv("AIGV_FUSED_LN");
-        h->fused_ln = !(e && e[0] == '0') && (h->D % 64 == 0) && h->stat_parts <= 32;
+        h->fused_ln = !(e && e[0] == '0') && (h->D % 64 == 0);
     }
 
     const size_t D = h->D, I = h->I, C = h->C;

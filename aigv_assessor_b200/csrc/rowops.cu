@@ -281,7 +281,8 @@ assemble_tokens_stats_kernel(const float* __restrict__ pe, const float* __restri
     }
     s = warp_sum(s);
     q = warp_sum(q);
-    if (lane < nparts) stats[static_cast<size_t>(lane) * M + row] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+    for (int p = lane; p < nparts; p += 32)
+        stats[static_cast<size_t>(p) * M + row] = p == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
 }
 
 // LayerNorm folded into the following Linear (run once per weight load):
@@ -457,7 +458,7 @@ cudaError_t launch_assemble_tokens(const float* pe, const float* cls, const floa
                                    cudaStream_t stream, __nv_bfloat16* xb, float2* stats, int nparts) {
     if (n <= 0 || (D % 4) != 0) return cudaErrorInvalidValue;
     if (xb || stats) {
-        if (!xb || !stats || nparts < 1 || nparts > 32) return cudaErrorInvalidValue;
+        if (!xb || !stats || nparts < 1) return cudaErrorInvalidValue;
         const int rows = n * (P + 1);
         assemble_tokens_stats_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(pe, cls, pos, x, xb, stats, nparts, n, P, D);
         return cudaGetLastError();

@@ -99,7 +99,7 @@ def test_gemm_residual_stats(M, N, K):
     x = dev(res.clone())
     da, dw, db, dl = dev(a), dev(w), dev(bias), dev(ls)
     parts = lib.aigv_stats_slices(N)
-    assert parts == (N + 127) // 128
+    assert parts == (N + 63) // 64
     xb = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
     stats = torch.full((parts, M, 2), float("nan"), device="cuda")
     st = lib.aigv_gemm_residual_stats(ptr(da), ptr(dw), ptr(db), ptr(dl), ptr(x), ptr(xb), ptr(stats), M, N, K, stream())
