@@ -150,3 +150,31 @@ def test_plugin_install_on_module_standin():
     plugin.uninstall(m)
     with pytest.raises(AssertionError):
         m.extract_feature(pv)
+
+
+def test_frames_to_tokens_dynamic_tiling_micro_batched():
+    """Config 4 shape of the path: uint8 frames -> dynamic tiling with thumbnail (7 tiles per frame) ->
+    tokens, through encode_frames, with the 14 tiles split over two micro-batches (max_tiles = 8). Oracle: the numpy front
+    end (bit-exact pixel_values) + the numpy tower on those pixel_values."""
+    from oracle import preprocess_oracle as po
+    cfg = tiny()
+    sd = synth.make_weights(cfg, seed=21)
+    eng = VisionEngine(cfg, max_tiles=8).load_state_dict(sd)
+    frames = synth.make_frames(2, 512, 768, seed=22, kind="smooth")
+    out = eng.encode_frames(torch.from_numpy(frames), max_num=6, use_thumbnail=True)
+    torch.cuda.synchronize()
+    tiles, ref_pv, counts = po.load_video_frames(frames, max_num=6, use_thumbnail=True)
+    assert counts == [7, 7] and out.shape == (14, 256, cfg.llm_hidden)
+    pv, got_counts = eng.preprocess_frames(torch.from_numpy(frames), max_num=6)
+    assert got_counts == counts
+    ref_bf16 = synth.bf16_round(np.asarray(ref_pv, dtype=np.float32))
+    assert np.array_equal(pv.float().cpu().numpy(), ref_bf16)  # front end bit-exact, thumbnail last in every frame
+    ref = vo.extract_feature(ref_bf16, sd, cfg)
+    e = vo.error_metrics(out.float().cpu().numpy(), ref)
+    print("frames->tokens (14 tiles, 2 micro-batches) e_max/e_l2", e)
+    assert e[0] < TOL
+    # micro-batching is invisible: the same tiles in one batch give the same bits
+    eng2 = VisionEngine(cfg, max_tiles=16).load_state_dict(sd)
+    out2 = eng2.extract_feature(pv)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
