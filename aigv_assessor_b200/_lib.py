@@ -13,7 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaigv_b200.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "rowops.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention2_tcgen05.cu", "rowops.cu", "preprocess.cu"]
 HEADERS = ["kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "aigv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -92,6 +92,7 @@ SIGNATURES = {
                                        C.c_int, C.c_int, _P]),
     "aigv_assemble_tokens_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "aigv_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "aigv_exp2_poly": (C.c_int, [_P, _P, C.c_int, _P]),
     "aigv_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "aigv_rmsnorm_inplace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_im2col": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

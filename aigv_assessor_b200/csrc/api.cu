@@ -59,15 +59,34 @@ static cudaError_t run_gemm(const CUtensorMap& a, const CUtensorMap& b, const CU
     return launch_gemm(a, b, c, M, N, K, ep, num_sms, st);
 }
 
+// SM count of the CURRENT device (cached per device: engines on different GPUs of one process each get their own).
 static int device_num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = v > 0 ? v : 148;
     }
-    return sms;
+    return sms[dev];
+}
+
+// Attention dispatcher: the round-2 persistent kernel by default; AIGV_ATTN_V1=1 selects the round-1 kernel (A/B runs;
+// it needs tokens % 64 <= 32).
+static bool attention_use_v1() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("AIGV_ATTN_V1");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+static cudaError_t run_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
+                                 const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads, int head_dim,
+                                 float scale, int num_sms, cudaStream_t st) {
+    if (attention_use_v1()) return launch_attention(tm_q, tm_kv, tm_tail, qkv, out, frames, S, heads, head_dim, scale, st);
+    return launch_attention2(tm_q, qkv, out, frames, S, heads, head_dim, scale, num_sms, st);
 }
 
 // ------------------------------------------------------------------------------------------------ dtype conversion
@@ -314,7 +333,8 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
     h->T = (h->g / 2) * (h->g / 2);
     if (h->hd != 64 && h->hd != 128)
         return bad(AIGV_ERR_UNSUPPORTED, "attention kernel covers head_dim 64 (InternViT-300M) and 128 (InternViT-6B)");
-    if (h->S % 64 > 32) return bad(AIGV_ERR_UNSUPPORTED, "attention kernel needs (tokens mod 64) <= 32");
+    if (attention_use_v1() && h->S % 64 > 32)
+        return bad(AIGV_ERR_UNSUPPORTED, "the round-1 attention kernel needs (tokens mod 64) <= 32");
     if (h->g % 2) return bad(AIGV_ERR_UNSUPPORTED, "patch grid must be even for the 2x2 pixel shuffle");
     if (h->D % 32 || h->I % 32 || h->C % 32 || cfg->patch_size % 2)
         return bad(AIGV_ERR_UNSUPPORTED, "hidden/intermediate/llm widths must be multiples of 32");
@@ -618,7 +638,8 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         if (h->cfg.qk_normalization) {
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st, w.knw, D), "q_norm+k_norm");
         }
-        AIGV_LAUNCH(K_ATTENTION, launch_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->qkv, h->attn, n, S, h->H, h->hd, scale, st),
+        AIGV_LAUNCH(K_ATTENTION, run_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->qkv, h->attn, n, S, h->H, h->hd, scale,
+                                               h->num_sms, st),
                  "attention");
         {
             GemmEpilogue ep;
@@ -890,14 +911,20 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
                    void* stream) {
     if (!qkv_bf16 || !out_bf16 || frames <= 0 || S <= 0 || heads <= 0) return AIGV_ERR_INVALID;
     if (head_dim != 64 && head_dim != 128) return AIGV_ERR_UNSUPPORTED;
-    if (S % 64 > 32) return AIGV_ERR_UNSUPPORTED;
+    if (attention_use_v1() && S % 64 > 32) return AIGV_ERR_UNSUPPORTED;
     const uint64_t M = (uint64_t)frames * S, D3 = 3ull * heads * head_dim;
     CUtensorMap tq, tk, tt;
     if (make_tmap_bf16_2d(&tq, qkv_bf16, M, D3, D3, attention_q_rows(), 64)) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tk, qkv_bf16, M, D3, D3, attention_kv_rows(), 64)) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tt, qkv_bf16, M, D3, D3, attention_tail_rows(S), 64)) return AIGV_ERR_INVALID;
-    AIGV_TRY0(launch_attention(tq, tk, tt, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
-                               static_cast<cudaStream_t>(stream)));
+    AIGV_TRY0(run_attention(tq, tk, tt, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
+                            device_num_sms(), static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_exp2_poly(const float* x, float* y, int n, void* stream) {
+    if (!x || !y || n <= 0) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_exp2_poly_test(x, y, n, static_cast<cudaStream_t>(stream)));
     return AIGV_OK;
 }
 

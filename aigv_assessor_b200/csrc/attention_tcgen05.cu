@@ -576,13 +576,10 @@ template <int HD>
 cudaError_t launch_attention_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
                                 const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads,
                                 float softmax_scale, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Geo<HD>::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long optin_mask = 0;  // per device (kernels.h)
+    cudaError_t e = ensure_smem_optin(reinterpret_cast<const void*>(&attention_fwd_kernel<HD>), Geo<HD>::SMEM_BYTES,
+                                      optin_mask);
+    if (e != cudaSuccess) return e;
     // side-row mode: S = k * 256 + 1 (k >= 1) -- the leftover query row rides on the producer warp of CTA 0
     const int side_row = (S > BQ * TILES && S % (BQ * TILES) == 1 && qkv != nullptr) ? 1 : 0;
     dim3 grid(side_row ? S / (BQ * TILES) : (S + BQ * TILES - 1) / (BQ * TILES), heads, frames);

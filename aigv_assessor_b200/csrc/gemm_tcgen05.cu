@@ -447,12 +447,9 @@ cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const
                            int M, int N, int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
     using C = Cfg<kEpiWarps, kResid>;
     auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32, kEpiWarps, kResid>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static unsigned long long optin_mask = 0;  // per device (kernels.h)
+    cudaError_t e = ensure_smem_optin(reinterpret_cast<const void*>(kern), C::SMEM_BYTES, optin_mask);
+    if (e != cudaSuccess) return e;
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     int pairs = num_sms / 2;
     if (tiles < pairs) pairs = tiles;

@@ -64,6 +64,27 @@ cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, 
                              const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads, int head_dim,
                              float softmax_scale, cudaStream_t stream);
 
+// Round-2 persistent kernel (attention2_tcgen05.cu): ONE map over the qkv matrix with a [attention2_box_rows(), 64] box
+// serves Q, K and V; any sequence length; head_dim 64 or 128; num_sms = persistent CTAs to launch.
+int attention2_box_rows();
+cudaError_t launch_attention2(const CUtensorMap& tm_qkv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S,
+                              int heads, int head_dim, float softmax_scale, int num_sms, cudaStream_t stream);
+
+// Test hook: y[i] = the attention kernel's FMA-pipe 2^x (exp2_poly2) for x[i] (softmax arguments are <= 8).
+cudaError_t launch_exp2_poly_test(const float* x, float* y, int n, cudaStream_t stream);
+
+// Opt a kernel in to > 48 KiB of dynamic shared memory once PER DEVICE (function attributes are per device: a second
+// engine on another GPU of the same process needs its own opt-in). `mask` is the call site's static bit set.
+inline cudaError_t ensure_smem_optin(const void* kernel, int bytes, unsigned long long& mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && ((mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) mask |= 1ull << dev;
+    return e;
+}
+
 // ---- row-wise / bandwidth kernels --------------------------------------------------------------------------------
 // y[r,:] = LN(x[r,:]) * w + b (b may be null -> RMSNorm when rms != 0). x fp32 [rows, D] -> y bf16 [rows, D].
 cudaError_t launch_norm_f32_to_bf16(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows, int D,

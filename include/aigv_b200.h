@@ -122,9 +122,13 @@ int aigv_gemm_norm_fused(const void* a_bf16, const void* wf_bf16, const float* w
                          void* stream);
 int aigv_assemble_tokens_stats(const float* pe, const float* cls, const float* pos, float* x, void* xb_bf16,
                                float* stats, int nparts, int n, int P, int D, void* stream);
-/* qkv bf16 [frames*S, 3*heads*head_dim] (three, head, d) -> out bf16 [frames*S, heads*head_dim]. */
+/* qkv bf16 [frames*S, 3*heads*head_dim] (three, head, d) -> out bf16 [frames*S, heads*head_dim]
+ * (flash_attention.py:52-55 / modeling_intern_vit.py:143-157). Any sequence length; head_dim 64 or 128. */
 int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int heads, int head_dim, float scale,
                    void* stream);
+/* Test hook: y[i] = 2^x[i] exactly as the attention kernel evaluates the share of its exponentials that runs on the
+ * FMA pipe instead of MUFU (Cody-Waite split + cubic; x fp32 [n], device pointers). */
+int aigv_exp2_poly(const float* x, float* y, int n, void* stream);
 int aigv_layernorm(const float* x, const float* w, const float* b, void* y_bf16, int rows, int D, float eps, int rms,
                    void* stream);
 int aigv_rmsnorm_inplace(void* x_bf16, const float* w, int rows, int D, int ld, int col0, float eps, void* stream);
