@@ -2,7 +2,7 @@
 ``extract_feature`` seam. See DESIGN.md / INTEGRATION.md."""
 from .config import VisionPathConfig, internvit_300m, internvit_6b, tiny  # noqa: F401
 
-__all__ = ["VisionPathConfig", "internvit_300m", "internvit_6b", "tiny", "VisionEngine", "install", "uninstall"]
+__all__ = ["VisionPathConfig", "internvit_300m", "internvit_6b", "tiny", "VisionEngine", "install", "refresh", "uninstall"]
 
 
 def __getattr__(name):  # torch-dependent pieces are imported lazily so config/synth stay importable anywhere
@@ -12,7 +12,7 @@ def __getattr__(name):  # torch-dependent pieces are imported lazily so config/s
     if name in ("metrics", "sharding", "tiling"):
         import importlib
         return importlib.import_module("." + name, __name__)
-    if name in ("install", "uninstall"):
+    if name in ("install", "refresh", "uninstall"):
         from . import plugin
         return getattr(plugin, name)
     raise AttributeError(name)

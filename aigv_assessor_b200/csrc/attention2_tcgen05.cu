@@ -35,7 +35,13 @@
 #include "ptx.cuh"
 
 #ifndef AIGV_ATTN_POLY
-#define AIGV_ATTN_POLY 2   // pairs out of every 4 pairs of exponentials evaluated on the FMA pipe (0..4)
+#define AIGV_ATTN_POLY 0   // pairs out of every 4 pairs of exponentials evaluated on the FMA pipe (0..4)
+#endif
+#ifndef AIGV_ATTN_ABL
+#define AIGV_ATTN_ABL 0   // timing ablations (WRONG results): 1 = no MUFU, 2 = no tcgen05.ld of S, 4 = no tcgen05.st of P, 8 = no row max
+#endif
+#ifndef AIGV_ATTN_PINGPONG
+#define AIGV_ATTN_PINGPONG 1   // the two softmax warps of an SM sub-partition take turns in their exponential phase
 #endif
 
 namespace aigv {
@@ -482,6 +488,13 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
         const int t = warp >> 2;                      // query tile of this warpgroup
         const int wq = warp & 3;                      // TMEM lane quadrant
         const int r = wq * 32 + lane;                 // row within the tile == TMEM lane
+        // Ping-pong (measured: without it the two softmax warps that share an SM sub-partition drift into lock step,
+        // both in their MUFU-heavy phase at once and both out of it at once: XU 66% busy). Warps w (tile 0) and w + 4
+        // (tile 1) sit on the same scheduler; named barrier 2 + 2*wq + t is "tile t's turn" of that pair: a warp waits
+        // for its turn before its exponentials and hands the turn over right after them, so one warp's tcgen05.ld /
+        // row max / tcgen05.st / barrier traffic runs under the other's exponentials. Tile 0 goes first.
+        const uint32_t pp_mine = 2 + 2 * wq + t, pp_other = 2 + 2 * wq + (t ^ 1);
+        if (AIGV_ATTN_PINGPONG && t == 1) named_bar_arrive(pp_other, 64);
         const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
         const uint32_t tm_o = tm_lane + TM_O + t * HD;
         uint32_t g_base = 0;     // (tile, block) steps of all earlier items
@@ -492,10 +505,15 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
             const Item m = decode_item(i, n_chunks, rot_div, H, S, smode);
             const int qb = it % QBUFS;
             const uint32_t qph = (it / QBUFS) & 1;
-            if (t >= m.n_t) {  // this warpgroup's tile holds no query row: only release Q
+            if (t >= m.n_t) {  // this warpgroup's tile holds no query row: only release Q (and keep passing the turn)
                 mbar_wait(&q_full[qb], qph);
                 if (lane == 0) mbar_arrive(&q_empty[qb]);
                 g_base += n_blocks * m.n_t;
+                if (AIGV_ATTN_PINGPONG)
+                    for (int j = 0; j < n_blocks; ++j) {
+                        named_bar_sync(pp_mine, 64);
+                        named_bar_arrive(pp_other, 64);
+                    }
                 continue;
             }
             const int tile_q0 = m.q0 + t * BQ;
@@ -514,17 +532,23 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                 tc_fence_after();
                 if (warp_live) {
                     uint32_t v[BKV];
+                    if (AIGV_ATTN_ABL & 2) {
 #pragma unroll
-                    for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(tm_s + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
-                    tmem_ld_wait();
+                        for (int c = 0; c < BKV; ++c) v[c] = __float_as_uint(-0.01f * (c + j) - l_run * 1e-30f);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(tm_s + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+                        tmem_ld_wait();
+                    }
                     if (j >= n_full) {  // masked tail block (never taken for ViT sequences)
 #pragma unroll
                         for (int c = 0; c < BKV; ++c)
                             if (c >= tail_valid) v[c] = 0xff800000u;
                     }
                     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                    if (AIGV_ATTN_ABL & 8) mx0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[77]));
 #pragma unroll
-                    for (int c = 0; c < BKV; c += 8) {
+                    for (int c = 0; c < ((AIGV_ATTN_ABL & 8) ? 0 : BKV); c += 8) {
                         mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
                         mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
                         mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])));
@@ -555,6 +579,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                         }
                         m_ref = new_ref;
                     }
+                    if (AIGV_ATTN_PINGPONG) named_bar_sync(pp_mine, 64);
                     // probabilities -> bf16 pairs written over the S buffer, row sum; packed fp32x2 arithmetic
                     const f32x2 sc2 = pack2(scale_log2, scale_log2), nm2 = pack2(-m_ref, -m_ref);
                     f32x2 sum01 = pack2(0.f, 0.f), sum23 = pack2(0.f, 0.f);
@@ -572,8 +597,13 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                                 } else {
                                     float x0, x1;
                                     unpack2(x, x0, x1);
-                                    p[2 * q] = ex2f(x0);
-                                    p[2 * q + 1] = ex2f(x1);
+                                    if (AIGV_ATTN_ABL & 1) {
+                                        p[2 * q] = x0;
+                                        p[2 * q + 1] = x1;
+                                    } else {
+                                        p[2 * q] = ex2f(x0);
+                                        p[2 * q + 1] = ex2f(x1);
+                                    }
                                 }
                             }
                             sum01 = add2(sum01, add2(pack2(p[0], p[1]), pack2(p[4], p[5])));
@@ -581,13 +611,22 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
 #pragma unroll
                             for (int q = 0; q < 4; ++q) pk[(e >> 1) + q] = pack_bf16x2(p[2 * q], p[2 * q + 1]);
                         }
-                        tmem_st_32x16(tm_s + (c >> 1), pk);
+                        if (AIGV_ATTN_ABL & 4) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) l_run += __uint_as_float(pk[e]) * 1e-30f;
+                        } else {
+                            tmem_st_32x16(tm_s + (c >> 1), pk);
+                        }
                     }
+                    if (AIGV_ATTN_PINGPONG) named_bar_arrive(pp_other, 64);
                     tmem_st_wait();
                     float s0, s1, s2, s3;
                     unpack2(sum01, s0, s1);
                     unpack2(sum23, s2, s3);
                     l_run += (s0 + s1) + (s2 + s3);
+                } else if (AIGV_ATTN_PINGPONG) {
+                    named_bar_sync(pp_mine, 64);
+                    named_bar_arrive(pp_other, 64);
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -55,6 +55,10 @@ class VisionEngine:
             raise ValueError("only select_layer=-1, downsample_ratio=0.5, ps_version='v2' are covered (SURVEY 8b)")
         self.cfg = cfg
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError(f"VisionEngine needs a CUDA device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = _lib.load()
         self.max_tiles = int(max_tiles)
         c = _lib.Cfg(cfg.hidden_size, cfg.num_heads, cfg.intermediate_size, cfg.num_layers, cfg.image_size,
@@ -124,15 +128,22 @@ class VisionEngine:
             ps_version=model.ps_version, select_layer=model.select_layer)
         dev = next(model.mlp1.parameters()).device
         eng = cls(cfg, max_tiles=max_tiles, device=dev if dev.type == "cuda" else None)
+        return eng.load_from_model(model)
+
+    def load_from_model(self, model) -> "VisionEngine":
+        """(Re-)ingest vision_model.* / mlp1.* from a live model, merging a peft-wrapped tower's LoRA."""
+        vsd = merge_lora_names(model.vision_model.state_dict())
         sd = {"vision_model." + k: v for k, v in vsd.items()}
-        sd.update({"mlp1." + k: v for k, v in m1.items()})
-        return eng.load_state_dict(sd)
+        sd.update({"mlp1." + k: v for k, v in model.mlp1.state_dict().items()})
+        return self.load_state_dict(sd)
 
     # ------------------------------------------------------------------ the hot path
     def extract_feature(self, pixel_values: torch.Tensor, flatten: bool = True,
                         out: torch.Tensor | None = None) -> torch.Tensor:
         """out (optional): a preallocated bf16 CUDA tensor [N, 256, C] to write into (avoids an allocation per call
-        when the caller pipelines copies on side streams)."""
+        when the caller pipelines copies on side streams).
+        The path computes in bf16 with fp32 accumulation whatever the input dtype (the reference's GPU dtype,
+        stage2_eval.py:932): fp32 / fp16 pixel_values are rounded to bf16 on entry and the result is cast back."""
         if pixel_values.dim() != 4:
             raise ValueError(f"wrong pixel_values size: {pixel_values.shape}")  # modeling_intern_vit.py:345
         cfg = self.cfg
@@ -141,6 +152,8 @@ class VisionEngine:
             raise ValueError(f"wrong pixel_values size: {pixel_values.shape}")
         if not pixel_values.is_cuda:
             raise ValueError("pixel_values must be a CUDA tensor (no CPU path)")
+        if pixel_values.device != self.device:
+            raise ValueError(f"pixel_values is on {pixel_values.device}, the engine (weights, workspace) on {self.device}")
         if not self._finalized:
             raise ValueError("weights not loaded")
         in_dtype = pixel_values.dtype
@@ -148,9 +161,9 @@ class VisionEngine:
         g2 = cfg.grid // 2
         if out is None:
             out = torch.empty((n, g2 * g2, cfg.llm_hidden), dtype=torch.bfloat16, device=pv.device)
-        elif (out.dtype != torch.bfloat16 or not out.is_cuda or not out.is_contiguous()
+        elif (out.dtype != torch.bfloat16 or out.device != self.device or not out.is_contiguous()
               or out.numel() != n * g2 * g2 * cfg.llm_hidden):
-            raise ValueError("out must be a contiguous bf16 CUDA tensor with N*256*C elements")
+            raise ValueError("out must be a contiguous bf16 tensor with N*256*C elements on the engine's device")
         else:
             out = out.view(n, g2 * g2, cfg.llm_hidden)
         if n:
@@ -165,8 +178,9 @@ class VisionEngine:
     def vit_hidden(self, n_tiles: int) -> torch.Tensor:
         """fp32 ViT last_hidden_state [n,1025,D] of the most recent micro-batch (tests)."""
         x = torch.empty((n_tiles, self.cfg.tokens, self.cfg.hidden_size), dtype=torch.float32, device=self.device)
-        st = self.lib.aigv_copy_vit_hidden(self._h, C.c_void_p(x.data_ptr()), n_tiles,
-                                           C.c_void_p(_stream_ptr(self.device)))
+        with torch.cuda.device(self.device):
+            st = self.lib.aigv_copy_vit_hidden(self._h, C.c_void_p(x.data_ptr()), n_tiles,
+                                               C.c_void_p(_stream_ptr(self.device)))
         _lib.check(st, self._h, "aigv_copy_vit_hidden")
         return x
 
@@ -178,7 +192,8 @@ class VisionEngine:
         """{kernel class: (total ms, launches)} measured with CUDA events on the launching stream."""
         k = self.lib.aigv_profile_num_classes()
         ms, cnt = (C.c_double * k)(), (C.c_int64 * k)()
-        _lib.check(self.lib.aigv_profile_read(self._h, ms, cnt, k, int(reset)), self._h, "aigv_profile_read")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.aigv_profile_read(self._h, ms, cnt, k, int(reset)), self._h, "aigv_profile_read")
         return {self.lib.aigv_profile_class_name(i).decode(): (ms[i], cnt[i]) for i in range(k) if cnt[i]}
 
     @property
@@ -196,6 +211,8 @@ class VisionEngine:
         t, hh, ww, _ = frames_u8.shape
         if not frames_u8.is_cuda:
             frames_u8 = frames_u8.to(self.device, non_blocking=True)
+        elif frames_u8.device != self.device:
+            raise ValueError(f"frames are on {frames_u8.device}, the engine on {self.device}")
         frames_u8 = frames_u8.contiguous()
         gi, gj = tiling.tile_grid(ww, hh, 1, max_num, self.cfg.image_size)
         per = gi * gj + (1 if (use_thumbnail and gi * gj != 1) else 0)

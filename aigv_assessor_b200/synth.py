@@ -130,3 +130,76 @@ def normalize_lut() -> np.ndarray:
     for c in range(3):
         lut[c] = (u - np.float32(IMAGENET_MEAN[c])) / np.float32(IMAGENET_STD[c])
     return lut
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Everything ABOVE the seam (test fixtures only): a small InternLM2 + motion_mlp + mlpscore under the reference's
+# state-dict names, so that score parity can be checked through the unchanged caller of extract_feature
+# (/root/reference/internvl/model/internvl_chat_eval2/modeling_internvl_chat.py:238-250,327-488). The reference hard-codes
+# 4096 for motion_mlp / mlpscore (eval2 :244-249,44), so the LLM width is 4096; depth / FFN width / vocabulary are small.
+HEAD_LLM = dict(hidden_size=4096, num_hidden_layers=2, num_attention_heads=32, num_key_value_heads=8,
+                intermediate_size=1024, vocab_size=512, rms_norm_eps=1e-5, rope_theta=1000000.0,
+                max_position_embeddings=32768)
+
+
+def head_weight_spec(llm: dict = HEAD_LLM):
+    H, I, V = llm["hidden_size"], llm["intermediate_size"], llm["vocab_size"]
+    hd = H // llm["num_attention_heads"]
+    qkv = (llm["num_attention_heads"] + 2 * llm["num_key_value_heads"]) * hd
+    lm = "language_model.model."
+    yield lm + "tok_embeddings.weight", (V, H), ("normal", 0.5, 0.0)
+    for i in range(llm["num_hidden_layers"]):
+        lp = f"{lm}layers.{i}."
+        yield lp + "attention.wqkv.weight", (qkv, H), ("uniform", H / 16.0)   # gain 4: peaked (not flat) attention, so score1 is sensitive to the visual tokens
+        yield lp + "attention.wo.weight", (H, H), ("uniform", H)
+        yield lp + "feed_forward.w1.weight", (I, H), ("uniform", H)
+        yield lp + "feed_forward.w3.weight", (I, H), ("uniform", H)
+        yield lp + "feed_forward.w2.weight", (H, I), ("uniform", I)
+        yield lp + "attention_norm.weight", (H,), ("normal", 0.1, 1.0)
+        yield lp + "ffn_norm.weight", (H,), ("normal", 0.1, 1.0)
+    yield lm + "norm.weight", (H,), ("normal", 0.1, 1.0)
+    yield "language_model.output.weight", (V, H), ("uniform", H)
+    yield "motion_mlp.0.weight", (2304,), ("normal", 0.1, 1.0)
+    yield "motion_mlp.0.bias", (2304,), ("normal", 0.1, 0.0)
+    yield "motion_mlp.1.weight", (4096, 2304), ("uniform", 2304)
+    yield "motion_mlp.1.bias", (4096,), ("uniform", 2304)
+    yield "motion_mlp.3.weight", (4096, 4096), ("uniform", 4096)
+    yield "motion_mlp.3.bias", (4096,), ("uniform", 4096)
+    # mlpscore (eval2 :43-94): ReLU after EVERY layer incl. the last, so zero-mean weights give score1 == 0. Weights are
+    # U(-b, b) as usual; the biases are positive so units stay alive, and fc5's weights are positive (score1 > 0).
+    dims = [H, 1024, 256, 64, 16, 1]
+    for l in range(5):
+        yield f"mlpscore.fc{l + 1}.weight", (dims[l + 1], dims[l]), (("uniform", dims[l] / 4.0) if l < 4 else ("posuniform", dims[l]))
+        yield f"mlpscore.fc{l + 1}.bias", (dims[l + 1],), ("normal", 0.02, 0.1 if l < 4 else 0.0)
+    yield "mlpscore.ln1.weight", (1024,), ("normal", 0.0, 1.0)   # constructed by the reference, never used in forward
+    yield "mlpscore.ln1.bias", (1024,), ("normal", 0.0, 0.0)
+
+
+def make_head_weights(seed: int = 0, llm: dict = HEAD_LLM) -> dict[str, np.ndarray]:
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: dict[str, np.ndarray] = {}
+    for name, shape, dist in head_weight_spec(llm):
+        if dist[0] == "uniform":
+            b = 1.0 / np.sqrt(dist[1])
+            sd[name] = bf16_round(rng.uniform(-b, b, size=shape).astype(np.float32))
+        elif dist[0] == "posuniform":
+            sd[name] = bf16_round(rng.uniform(0.0, 2.0 / np.sqrt(dist[1]), size=shape).astype(np.float32))
+        else:
+            sd[name] = bf16_round((dist[2] + dist[1] * rng.standard_normal(size=shape)).astype(np.float32))
+    return sd
+
+
+IMG_CONTEXT_ID, IMG_START_ID, IMG_END_ID = 7, 10, 11
+
+
+def make_clip_prompt(n_frames: int, tokens_per_frame: int = 256, n_text: int = 40, seed: int = 0,
+                     vocab_size: int = 512) -> np.ndarray:
+    """Token ids with the call shape of the video prompt (stage1_eval.py:477-494): <s>, per frame <img> + 256 x
+    <IMG_CONTEXT> + </img>, one more <img><IMG_CONTEXT></img> for the motion token, then text."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ids = [1]
+    for _ in range(n_frames):
+        ids += [IMG_START_ID] + [IMG_CONTEXT_ID] * tokens_per_frame + [IMG_END_ID]
+    ids += [IMG_START_ID, IMG_CONTEXT_ID, IMG_END_ID]
+    ids += [int(t) for t in rng.integers(20, vocab_size, size=n_text)]
+    return np.asarray([ids], dtype=np.int64)

@@ -1,0 +1,60 @@
+"""Score parity THROUGH the seam (BASELINE.json north_star: "final per-dimension quality scores within 0.02 absolute").
+
+The visual tokens come from the CUDA path; everything above the seam is the reference's arithmetic (oracle/head_oracle.py,
+pinned in tests/test_oracle_golden.py against the unmodified internvl_chat_eval2.InternVLChatModel run on CPU by
+tests/golden/make_golden_full.py): <IMG_CONTEXT> splice, motion token, InternLM2 prefill, mlpscore. The goldens hold the
+reference's own score1 / logits for the same seeded weights, frames and prompt."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from aigv_assessor_b200 import synth
+from aigv_assessor_b200.config import VisionPathConfig
+from aigv_assessor_b200.engine import VisionEngine
+from oracle import head_oracle as ho
+from oracle import vit_oracle as vo
+
+pytestmark = pytest.mark.gpu
+SCORE_TOL = 0.02
+
+
+def _case(golden_dir, name):
+    with open(os.path.join(golden_dir, "golden_meta_full.json")) as f:
+        meta = json.load(f)[name]
+    g = np.load(os.path.join(golden_dir, f"full_{name}.npz"))
+    cfg = VisionPathConfig(**meta["vis_cfg"])
+    sd_vis = synth.make_weights(cfg, seed=meta["seeds"]["vis"])
+    sd_head = synth.make_head_weights(seed=meta["seeds"]["head"])
+    sd_head["mlpscore.fc5.weight"] = synth.bf16_round(sd_head["mlpscore.fc5.weight"] * np.float32(meta["fc5_scale"]))
+    pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["seeds"]["x"])
+    ids = synth.make_clip_prompt(meta["n_frames"], seed=meta["seeds"]["ids"], vocab_size=meta["llm"]["vocab_size"])
+    return meta, g, cfg, sd_vis, sd_head, pv, ids
+
+
+@pytest.mark.parametrize("name", ["tiny", "vit300m"])
+def test_score1_and_logits_through_the_seam(golden_dir, name):
+    meta, g, cfg, sd_vis, sd_head, pv, ids = _case(golden_dir, name)
+    eng = VisionEngine(cfg, max_tiles=8).load_state_dict(sd_vis)
+    emb = eng.extract_feature(torch.from_numpy(pv).to(torch.bfloat16).cuda())
+    torch.cuda.synchronize()
+    emb = emb.float().cpu().numpy()
+    e_emb = float(np.abs(emb[:, ::8, ::16] - g["vit_embeds_s"]).max() / meta["vit_absmax"])
+    o = ho.stage2_forward(emb, pv, ids, ho.to_torch(sd_head), meta["llm"], synth.IMG_CONTEXT_ID)
+    d_score = abs(float(o["score1"][0]) - float(g["score1"][0]))
+    e_hid = vo.error_metrics(o["hidden_m4"], g["hidden_m4"])
+    # answer-span logits: identical argmax wherever the reference's own top-2 margin is not a numerical tie
+    ref_logits = g["logits_tail"]
+    top2 = np.sort(ref_logits, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 1e-2 * np.abs(ref_logits).max()
+    same = o["logit"][-48:] == g["logit_tail"]
+    print(f"{name}: reference score1 {float(g['score1'][0]):.4f}  CUDA-embeddings score1 {float(o['score1'][0]):.4f} "
+          f"|d| {d_score:.2e} (tol {SCORE_TOL}; a 1e-2 token perturbation moves it {meta['score_sensitivity_1e2']:.3f}); "
+          f"embeddings e_max {e_emb:.2e}; hidden[-4] e_max/e_l2 {e_hid}; logits argmax equal {int(same.sum())}/48 "
+          f"({int(decided.sum())} decided)")
+    assert e_emb < 2e-2
+    assert float(g["score1"][0]) > 1.0           # the ReLU head is not in its degenerate 0 regime
+    assert d_score <= SCORE_TOL
+    assert same[decided].all()

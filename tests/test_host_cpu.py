@@ -114,3 +114,40 @@ def test_gather_clip_results_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_plugin_rank_decision_on_the_six_real_variants():
+    """_variant_flattens runs each REAL variant class's own extract_feature on a 2x2-token stand-in: the stage-2 family
+    returns [N,256,C] (eval2 :527), internvl_chat / eval1 / stage1_lora keep [N,16,16,C] (internvl_chat :406-408)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden as mg
+    mg.install_stubs()
+    import importlib
+    from aigv_assessor_b200 import plugin
+    expect = {"internvl_chat": False, "internvl_chat_eval1": False, "internvl_chat_stage1_lora": False,
+              "internvl_chat_eval2": True, "internvl_chat_stage2": True, "internvl_chat_stage2_lora": True}
+    for variant, flat in expect.items():
+        mod = importlib.import_module(f"internvl.model.{variant}.modeling_internvl_chat")
+        cls = mod.InternVLChatModel
+        obj = object.__new__(cls)  # no __init__: the probe never touches real weights
+        assert plugin._variant_flattens(obj) is flat, variant
+
+
+def test_plugin_falls_back_while_training_and_refuses_other_configs():
+    import types
+    from aigv_assessor_b200 import plugin
+
+    class M:
+        select_layer, downsample_ratio, ps_version = -2, 0.5, "v2"
+
+        def extract_feature(self, pv):
+            return "original"
+
+    m = M()
+    assert plugin.install(m) is None and m.extract_feature(None) == "original"   # select_layer != -1: untouched
+    with pytest.raises(ValueError):
+        plugin.refresh(m)

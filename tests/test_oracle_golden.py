@@ -101,3 +101,35 @@ def test_torch_oracle_matches_reference_goldens(golden_dir, golden_meta, name):
     else:
         assert vo.error_metrics(vit.numpy()[:, ::41, ::16], g["vit_out_s"])[0] < 1e-5
         assert vo.error_metrics(out.numpy()[:, ::8, ::16], g["out_s"])[0] < 1e-5
+
+
+def _full_case(golden_dir, name):
+    import json
+    with open(os.path.join(golden_dir, "golden_meta_full.json")) as f:
+        meta = json.load(f)[name]
+    g = np.load(os.path.join(golden_dir, f"full_{name}.npz"))
+    cfg = VisionPathConfig(**meta["vis_cfg"])
+    sd_vis = synth.make_weights(cfg, seed=meta["seeds"]["vis"])
+    sd_head = synth.make_head_weights(seed=meta["seeds"]["head"])
+    sd_head["mlpscore.fc5.weight"] = synth.bf16_round(sd_head["mlpscore.fc5.weight"] * np.float32(meta["fc5_scale"]))
+    pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["seeds"]["x"])
+    ids = synth.make_clip_prompt(meta["n_frames"], seed=meta["seeds"]["ids"], vocab_size=meta["llm"]["vocab_size"])
+    return meta, g, cfg, sd_vis, sd_head, pv, ids
+
+
+def test_full_model_score_oracle_matches_reference(golden_dir):
+    """vit oracle -> head oracle reproduces the UNMODIFIED reference stage-2 forward (tests/golden/make_golden_full.py:
+    the real internvl_chat_eval2.InternVLChatModel on CPU): score1, its pre-ReLU value, hidden_states[-1][:, -4] and the
+    argmax of the shifted logits for one 8-frame clip."""
+    from oracle import head_oracle as ho
+    meta, g, cfg, sd_vis, sd_head, pv, ids = _full_case(golden_dir, "tiny")
+    emb = vo.extract_feature(pv, sd_vis, cfg)
+    assert vo.error_metrics(emb[:, ::8, ::16], g["vit_embeds_s"])[0] < 1e-5
+    o = ho.stage2_forward(emb, pv, ids, ho.to_torch(sd_head), meta["llm"], synth.IMG_CONTEXT_ID)
+    assert ids.shape[1] == meta["n_tokens"] and (ids == synth.IMG_CONTEXT_ID).sum() == 8 * 256 + 1
+    assert abs(float(o["score1"][0]) - float(g["score1"][0])) < 1e-3 and float(g["score1"][0]) > 1.0
+    assert abs(float(o["score_pre"][0]) - float(g["score_pre"][0])) < 1e-3
+    assert vo.error_metrics(o["hidden_m4"], g["hidden_m4"])[0] < 1e-4
+    assert np.array_equal(o["logit"][-48:], g["logit_tail"])
+    # the +-0.02 score tolerance is not vacuous: a 1e-2 (of max) gaussian perturbation of the tokens moves score1 this much
+    assert meta["score_sensitivity_1e2"] > 0.02
