@@ -12,6 +12,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: one range per launch of the path (no-ops without a profiler)
+
 #include "../../include/aigv_b200.h"
 #include "kernels.h"
 
@@ -82,11 +84,12 @@ static bool attention_use_v1() {
     }
     return v == 1;
 }
+// tm_q: [128, 64] boxes; tm_kv / tm_tail: the round-1 kernel's 64- and 32-row boxes; tm_kv2: the round-2 K/V box.
 static cudaError_t run_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
-                                 const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads, int head_dim,
-                                 float scale, int num_sms, cudaStream_t st) {
+                                 const CUtensorMap& tm_kv2, const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S,
+                                 int heads, int head_dim, float scale, int num_sms, cudaStream_t st) {
     if (attention_use_v1()) return launch_attention(tm_q, tm_kv, tm_tail, qkv, out, frames, S, heads, head_dim, scale, st);
-    return launch_attention2(tm_q, qkv, out, frames, S, heads, head_dim, scale, num_sms, st);
+    return launch_attention2(tm_q, tm_kv2, qkv, out, frames, S, heads, head_dim, scale, num_sms, st);
 }
 
 // ------------------------------------------------------------------------------------------------ dtype conversion
@@ -137,7 +140,7 @@ struct LayerW {
 
 struct ActMaps {
     int n = -1;
-    CUtensorMap patches, xn, attn, h, ps, m1, qkv_q, qkv_kv, qkv_tail;   // TMA loads (GEMM A operands, attention)
+    CUtensorMap patches, xn, attn, h, ps, m1, qkv_q, qkv_kv, qkv_tail, qkv_kv2;   // TMA loads (GEMM A operands, attention)
     CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out, xb_out;      // TMA stores / reduce-adds (GEMM outputs)
 };
 
@@ -256,6 +259,7 @@ int build_act_maps(aigv_handle* h, int n) {
     r |= make_tmap_bf16_2d(&h->maps.qkv_q, h->qkv, M, 3 * h->D, 3 * h->D, attention_q_rows(), 64);
     r |= make_tmap_bf16_2d(&h->maps.qkv_kv, h->qkv, M, 3 * h->D, 3 * h->D, attention_kv_rows(), 64);
     r |= make_tmap_bf16_2d(&h->maps.qkv_tail, h->qkv, M, 3 * h->D, 3 * h->D, attention_tail_rows(h->S), 64);
+    r |= make_tmap_bf16_2d(&h->maps.qkv_kv2, h->qkv, M, 3 * h->D, 3 * h->D, attention2_kv_box_rows(h->hd), 64);
     const int cr = gemm_box_rows_c(), cb = gemm_box_cols_c(false), cf = gemm_box_cols_c(true);
     r |= make_tmap_2d(&h->maps.pe_out, h->pe, 1, Mp, h->D, h->D, cr, cf);
     r |= make_tmap_2d(&h->maps.x_out, h->x, 1, M, h->D, h->D, cr, cf);
@@ -564,6 +568,7 @@ struct ProfScope {
     ProfRec* rec = nullptr;
     ProfScope(aigv_handle* h_, int cls, cudaStream_t st_) : h(h_), st(st_) {
         h->launches++;
+        nvtxRangePushA(kClassNames[cls]);  // an NVTX range per fused op
         if (!h->prof.on) return;
         Profiler& p = h->prof;
         if (p.used == p.pool.size()) {
@@ -577,6 +582,7 @@ struct ProfScope {
     }
     ~ProfScope() {
         if (rec) cudaEventRecord(rec->b, st);
+        nvtxRangePop();
     }
 };
 }  // namespace
@@ -638,7 +644,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         if (h->cfg.qk_normalization) {
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st, w.knw, D), "q_norm+k_norm");
         }
-        AIGV_LAUNCH(K_ATTENTION, run_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->qkv, h->attn, n, S, h->H, h->hd, scale,
+        AIGV_LAUNCH(K_ATTENTION, run_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->maps.qkv_kv2, h->qkv, h->attn, n, S, h->H, h->hd, scale,
                                                h->num_sms, st),
                  "attention");
         {
@@ -774,10 +780,24 @@ int aigv_tile_grid(int width, int height, int min_num, int max_num, int image_si
     return AIGV_OK;
 }
 
+// Tap tables of one (source size, target size) pair, built on the host like Pillow's precompute_coeffs and cached on the
+// device. The FIRST call for a new size synchronises (cudaMalloc + blocking uploads); later calls are asynchronous. The
+// cache is bounded: beyond kMaxPlans sizes it is flushed (after a device synchronise, so no launch still reads a table).
+static const size_t kMaxPlans = 64;
 static int get_plan(aigv_handle* h, int H, int W, int out_w, int out_h, PlanDev** out) {
     auto key = std::make_tuple(H, W, out_w, out_h);
     auto it = h->plans.find(key);
     if (it != h->plans.end()) { *out = &it->second; return 0; }
+    if (h->plans.size() >= kMaxPlans) {
+        cudaDeviceSynchronize();
+        for (auto& kv : h->plans) {
+            for (void* q : {(void*)kv.second.kx, (void*)kv.second.bx, (void*)kv.second.ky, (void*)kv.second.by}) {
+                cudaFree(q);
+                h->allocs.erase(std::remove(h->allocs.begin(), h->allocs.end(), q), h->allocs.end());
+            }
+        }
+        h->plans.clear();
+    }
     std::vector<int32_t> kx, bx, ky, by;
     PlanDev p;
     p.ksize_x = plan_axis(W, out_w, kx, bx);
@@ -809,12 +829,18 @@ int aigv_preprocess_u8(aigv_handle* h, const uint8_t* frames, int n, int H, int 
     const int per_frame = blocks + (with_thumb ? 1 : 0);
     PlanDev* p = nullptr;
     if (get_plan(h, H, W, tile * gi, tile * gj, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
+    if (!preprocess_fits(p->max_rows, p->span_bytes))
+        return fail(h, AIGV_ERR_UNSUPPORTED, "frame too large for the resize kernel's shared-memory window (" +
+                                                 std::to_string(W) + "x" + std::to_string(H) + " -> " + std::to_string(tile * gi) + "x" +
+                                                 std::to_string(tile * gj) + "): down-scale factors up to about 8x (4K sources) are covered");
     ResizePlan rp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile * gi, tile * gj};
     AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, rp, p->max_rows, p->span_bytes, h->lut, tile, gi,
                                     per_frame, 0, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
              "preprocess");
     if (with_thumb) {
         if (get_plan(h, H, W, tile, tile, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
+        if (!preprocess_fits(p->max_rows, p->span_bytes))
+            return fail(h, AIGV_ERR_UNSUPPORTED, "frame too large for the thumbnail resize's shared-memory window");
         ResizePlan tp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile, tile};
         AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, tp, p->max_rows, p->span_bytes, h->lut, tile, 1,
                                         per_frame, blocks, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
@@ -913,11 +939,12 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
     if (head_dim != 64 && head_dim != 128) return AIGV_ERR_UNSUPPORTED;
     if (attention_use_v1() && S % 64 > 32) return AIGV_ERR_UNSUPPORTED;
     const uint64_t M = (uint64_t)frames * S, D3 = 3ull * heads * head_dim;
-    CUtensorMap tq, tk, tt;
+    CUtensorMap tq, tk, tt, tk2;
     if (make_tmap_bf16_2d(&tq, qkv_bf16, M, D3, D3, attention_q_rows(), 64)) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tk, qkv_bf16, M, D3, D3, attention_kv_rows(), 64)) return AIGV_ERR_INVALID;
     if (make_tmap_bf16_2d(&tt, qkv_bf16, M, D3, D3, attention_tail_rows(S), 64)) return AIGV_ERR_INVALID;
-    AIGV_TRY0(run_attention(tq, tk, tt, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
+    if (make_tmap_bf16_2d(&tk2, qkv_bf16, M, D3, D3, attention2_kv_box_rows(head_dim), 64)) return AIGV_ERR_INVALID;
+    AIGV_TRY0(run_attention(tq, tk, tt, tk2, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
                             device_num_sms(), static_cast<cudaStream_t>(stream)));
     return AIGV_OK;
 }

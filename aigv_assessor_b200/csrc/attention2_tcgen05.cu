@@ -6,29 +6,37 @@
 //
 // What changed against the round-1 kernel (attention_tcgen05.cu) and why (profiles/r1f_ncu_attn_summary.txt: XU 54%,
 // tensor 27%, 39% of the softmax warps' samples waiting for S): the per-tile chain softmax(j) -> P V(j) -> Q K^T(j+1)
-// was serial because P aliased the only S buffer of a tile, every exponential went through MUFU, and a 64-key block
-// paid one commit -> mbarrier -> tcgen05.ld round trip per 64 exps per thread.
-//   * ONE persistent CTA per SM walks a list of work items (frame, head, 256 query rows = two 128-row tiles).
-//     Barriers, TMEM and descriptors are set up once; the loads / Q K^T of item i+1 overlap the epilogue of item i.
-//   * 128-key blocks: one query row per thread holds the 128 scores of a block in registers (one tcgen05.ld pass, half
-//     as many round trips); the softmax warpgroups get 208 registers through setmaxnreg, the four service warps 88.
-//   * head_dim 64: THREE S buffers rotate over the two tiles (512 TMEM columns = 3 x 128 S/P + 2 x 64 O). The MMA warp
-//     keeps Q K^T three (tile, block) steps ahead of P V, so when a warpgroup has written P(j) its S(j+1) is already
-//     in TMEM: the tensor-pipe latency leaves the per-tile chain. head_dim 128 has room for two S buffers
-//     (2 x 128 + 2 x 128 columns) and keeps the alternating schedule.
-//   * AIGV_ATTN_POLY of every 4 pairs of exponentials are evaluated on the FMA pipe (Cody-Waite split + cubic minimax
-//     polynomial of 2^f on [-0.5, 0.5], |rel err| <= 7.5e-5, 26x below the bf16 rounding of P) with packed FFMA2.
-//   warp 8: TMA producer   warp 9: MMA issuer   warps 10/11: the class-token query row (see below)
-//   warps 0-3 / 4-7: softmax warpgroup of query tile 0 / 1, one query row per thread (TMEM lane == row).
+// was serial because P aliased the only S buffer of a tile, so every block paid a commit -> mbarrier -> tcgen05.ld
+// round trip that four warps per scheduler could not cover.
+//   * ONE persistent CTA per SM walks a list of work items (frame, head, TILES x 128 query rows). Barriers, TMEM and
+//     descriptors are set up once; the loads / Q K^T of item i+1 overlap the epilogue of item i.
+//   * More S buffers than tiles, rotating: the MMA warp keeps Q K^T NSB (tile, block) steps ahead of P V, so when a
+//     warpgroup has written P(j) its S(j+1) is already in TMEM -- the tensor-pipe latency leaves the per-tile chain.
+//     head_dim 64:  3 tiles x 64-key blocks, 5 S/P buffers  (5 x 64 + 3 x 64 O columns = 512 TMEM columns); three
+//                   softmax warps per scheduler, one query row per thread, the block's 64 scores in registers
+//                   (one tcgen05.ld pass instead of round 1's two);
+//     head_dim 128: 2 tiles x 128-key blocks, 2 S/P buffers (2 x 128 + 2 x 128), the alternating schedule.
+//     (Measured on the way, profiles/r2_attention_notes.txt: with two tiles x 128-key blocks x 3 buffers at d = 64 the
+//     period of a scheduler's two softmax warps was N + E -- the non-MUFU part N of a block, ~1700 cycles, never hid
+//     under the partner's exponentials E -- 390 us against 451 us for round 1; a third warp per scheduler hides N.)
+//   * The softmax warps of a scheduler take turns in their exponential phase (named barriers): one warp's tcgen05.ld /
+//     row max / tcgen05.st / mbarrier traffic runs under another's MUFU stream instead of all competing for it.
+//   * The MMA issuer's instruction stream sits between a warpgroup's P and its later S: ring indices / parities are
+//     running counters, descriptors one add from constants, P V(g) and Q K^T(g + NSB) leave from one elected region.
+//   * AIGV_ATTN_POLY (default 0) of every 4 pairs of exponentials can be evaluated on the FMA pipe (Cody-Waite split +
+//     cubic minimax polynomial of 2^f on [-0.5, 0.5], |rel err| <= 7.5e-5). Measured: it LOSES here -- the packed FMA
+//     work costs more issue slots than the MUFU slots it frees -- so it is off; aigv_exp2_poly keeps it tested.
+//   warp 4T: TMA producer   warp 4T+1: MMA issuer   warps 4T+2/3: the class-token query row (see below)
+//   warps 4t..4t+3: softmax warpgroup of query tile t, one query row per thread (TMEM lane == row).
 // O lives in TMEM for the whole KV loop of an item. m_ref is a *stale* row maximum: it is only raised (and O, l
 // rescaled through tcgen05.ld/st, after waiting for the tile's previous P V) when the true running maximum exceeds it
 // by more than 2^8, so p <= 256 always and the rescale is rare; the final O / l is exact regardless of the reference.
-// Ragged ends. Keys: S % 128 == 1 (every ViT sequence: 1024 patches + the class token): the lone tail key never
+// Ragged ends. Keys: S % BKV == 1 (every ViT sequence: 1024 patches + the class token): the lone tail key never
 // enters the tensor pipeline -- its k / v rows sit in shared memory as fp32 and every query row folds it in during its
 // epilogue (a head_dim-term dot product with its own Q row, an exact max/alpha update, O*alpha + p*v). Any other tail
-// is one more (masked) block. Queries: S % 256 == 1: the class-token row rides on warps 10/11 of the CTA that owns the
-// first 256 rows of that (frame, head) -- fp32 online softmax on the CUDA cores from the very K/V stages the tensor
-// pipe consumes, 64 keys of every block per warp -- so the grid has exactly S/256 items per (frame, head).
+// is one more (masked) block. Queries: S % 128 == 1: the class-token row rides on the two side warps of the CTA that
+// owns the first rows of that (frame, head) -- fp32 online softmax on the CUDA cores from the very K/V stages the
+// tensor pipe consumes, half of every block's keys per warp -- so no tile is spent on one row.
 // A masked tail block multiplies P == 0 with V rows of the NEXT frame (TMA zero-fills past the end of the matrix);
 // with finite activations that contributes exactly nothing.
 #include "kernels.h"
@@ -37,49 +45,60 @@
 #ifndef AIGV_ATTN_POLY
 #define AIGV_ATTN_POLY 0   // pairs out of every 4 pairs of exponentials evaluated on the FMA pipe (0..4)
 #endif
-#ifndef AIGV_ATTN_ABL
-#define AIGV_ATTN_ABL 0   // timing ablations (WRONG results): 1 = no MUFU, 2 = no tcgen05.ld of S, 4 = no tcgen05.st of P, 8 = no row max
+#ifndef AIGV_ATTN_TILES64
+#define AIGV_ATTN_TILES64 2   // head_dim 64 geometry: 2 = two tiles x 128-key blocks x 3 S buffers; 3 = three tiles x 64 x 5
+#endif
+#ifndef AIGV_ATTN_MMA1T
+#define AIGV_ATTN_MMA1T 0   // 1: one elected thread runs the whole MMA-issuer loop (no per-step elect / reconvergence)
 #endif
 #ifndef AIGV_ATTN_PINGPONG
-#define AIGV_ATTN_PINGPONG 1   // the two softmax warps of an SM sub-partition take turns in their exponential phase
+#define AIGV_ATTN_PINGPONG 1   // the softmax warps of an SM sub-partition take turns in their exponential phase
 #endif
 
 namespace aigv {
 
 namespace {
 
-constexpr int BQ = 128;     // query rows per tile
-constexpr int TILES = 2;    // query tiles per work item
-constexpr int CHUNK = BQ * TILES;
-constexpr int BKV = 128;    // keys per block
-constexpr int SOFTMAX_WARPS = 4 * TILES;
-constexpr int WARP_PRODUCER = SOFTMAX_WARPS, WARP_MMA = SOFTMAX_WARPS + 1, WARP_SIDE = SOFTMAX_WARPS + 2;
-constexpr int THREADS = (SOFTMAX_WARPS + 4) * 32;   // three warpgroups (setmaxnreg works per warpgroup)
-constexpr int REGS_SOFTMAX = 208, REGS_SERVICE = 88;  // 2*128*208 + 128*88 = 64512 <= 384 * 168
-constexpr float RESCALE_THRESHOLD = 8.0f;           // log2 units
+constexpr int BQ = 128;                    // query rows per tile
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 template <int HD>
 struct Geo2 {
+    static constexpr bool T3 = HD == 64 && AIGV_ATTN_TILES64 == 3;
+    static constexpr int TILES = T3 ? 3 : 2;              // query tiles per work item
+    static constexpr int BKV = T3 ? 64 : 128;             // keys per block
+    static constexpr int NSB = T3 ? 5 : (HD == 64 ? 3 : 2);  // S/P buffers in TMEM (>= TILES)
+    static constexpr int PVR = NSB <= 2 ? 2 : (NSB <= 4 ? 4 : 8);  // ring of "P V done" barriers per tile (>= NSB, power of 2)
+    static constexpr int CHUNK = BQ * TILES;
+    static constexpr int SOFTMAX_WARPS = 4 * TILES;
+    static constexpr int WARP_PRODUCER = SOFTMAX_WARPS, WARP_MMA = SOFTMAX_WARPS + 1, WARP_SIDE = SOFTMAX_WARPS + 2;
+    static constexpr int THREADS = (SOFTMAX_WARPS + 4) * 32;  // whole warpgroups (setmaxnreg works per warpgroup)
+    // registers after setmaxnreg: 12*32*144 + 4*32*80 = 65536 (launch: 512 x 128); 8*32*208 + 4*32*88 = 64512 (384 x 168)
+    static constexpr int REGS_SOFTMAX = T3 ? 144 : 208;
+    static constexpr int REGS_SERVICE = T3 ? 80 : 88;
     static constexpr int ATOMS = HD / 64;                 // 64-column (128-byte) swizzle atoms per operand row
     static constexpr int Q_ATOM = BQ * 128;               // 16 KiB
-    static constexpr int KV_ATOM = BKV * 128;             // 16 KiB
+    static constexpr int KV_ATOM = BKV * 128;             // 8 / 16 KiB
     static constexpr int Q_BYTES = ATOMS * Q_ATOM;
     static constexpr int KV_BYTES = ATOMS * KV_ATOM;
-    static constexpr int NSB = HD == 64 ? 3 : 2;          // S/P buffers in TMEM
-    static constexpr int STAGES = HD == 64 ? 4 : 2;       // K / V ring depth
+    static constexpr int STAGES = T3 ? 6 : (HD == 64 ? 4 : 2);  // K / V ring depth
     static constexpr int QBUFS = HD == 64 ? 2 : 1;        // Q tiles of the next item land while this one computes
+    static constexpr int KPW = BKV / 2;                   // keys of a block per side warp
     static constexpr int OFF_Q = 0;
     static constexpr int OFF_K = OFF_Q + QBUFS * TILES * Q_BYTES;
     static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
     static constexpr int OFF_BAR = OFF_V + STAGES * KV_BYTES;
     static constexpr int OFF_SIDE = OFF_BAR + 512;
     // fp32 side region: [2][2*HD] lone tail key k, v (ring of two items) | [2][HD] q of the class-token row (one copy
-    // per side warp) | [2][64] its probabilities | [HD + 32] merge buffer of the second side warp
-    static constexpr int SIDE_FLOATS = 2 * 2 * HD + 2 * HD + 2 * 64 + HD + 32;
+    // per side warp) | [2][KPW] its probabilities | [HD + 32] merge buffer of the second side warp
+    static constexpr int SIDE_FLOATS = 2 * 2 * HD + 2 * HD + 2 * KPW + HD + 32;
     static constexpr int SMEM_BYTES = OFF_SIDE + SIDE_FLOATS * 4;
     static constexpr uint32_t TM_O = NSB * BKV;           // O accumulators behind the S buffers
     static constexpr uint32_t TMEM_COLS = 512;
     static_assert(NSB * BKV + TILES * HD <= 512, "TMEM budget");
+    static_assert(NSB >= TILES, "every tile needs an S buffer of its own");
+    static_assert((2 * QBUFS + 4 * STAGES + 2 * NSB + TILES * PVR + TILES) * 8 + 8 <= 512, "barrier region");
+    static_assert(2 + 4 * TILES <= 16, "named barriers of the exponential turn");
 };
 
 struct Item {
@@ -88,8 +107,10 @@ struct Item {
 };
 
 // item index -> (frame, head, chunk). Items of one (frame, head) are adjacent (their CTAs share K/V in L2); the chunk is
-// rotated by the pass number so the CTA that gets the class-token row changes from pass to pass.
-__device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, int H, int S, bool side_mode) {
+// rotated by the pass number so the CTA that gets the class-token row changes from pass to pass. s_rows = rows that
+// tiles cover (the sequence without the class-token side row).
+template <int CHUNK, int TILES>
+__device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, int H, int S, int s_rows, bool side_mode) {
     Item m;
     const int fh = i / n_chunks;
     const int raw = i - fh * n_chunks;
@@ -98,7 +119,8 @@ __device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, in
     m.head = fh - m.frame * H;
     m.q0 = chunk * CHUNK;
     m.row_base = m.frame * S;
-    m.n_t = (m.q0 + BQ < S) ? TILES : 1;
+    const int left = s_rows - m.q0;
+    m.n_t = left >= CHUNK ? TILES : (left + BQ - 1) / BQ;
     m.side = side_mode && chunk == 0;
     return m;
 }
@@ -143,14 +165,16 @@ __device__ __forceinline__ void exp2_poly2(f32x2 x, float& p0, float& p1) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(THREADS, 1)
-attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfloat16* __restrict__ qkv,
-                      __nv_bfloat16* __restrict__ out, int S, int H, int n_items, int n_chunks, int rot_div,
-                      int side_mode, float scale_log2) {
+__global__ void __launch_bounds__(Geo2<HD>::THREADS, 1)
+attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                      const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int H, int n_items,
+                      int n_chunks, int rot_div, int side_mode, float scale_log2) {
     using G = Geo2<HD>;
+    constexpr int TILES = G::TILES, BKV = G::BKV, CHUNK = G::CHUNK, SOFTMAX_WARPS = G::SOFTMAX_WARPS,
+                  WARP_PRODUCER = G::WARP_PRODUCER, WARP_MMA = G::WARP_MMA, WARP_SIDE = G::WARP_SIDE, KPW = G::KPW;
     constexpr int ATOMS = G::ATOMS, Q_ATOM = G::Q_ATOM, KV_ATOM = G::KV_ATOM, Q_BYTES = G::Q_BYTES,
                   KV_BYTES = G::KV_BYTES, NSB = G::NSB, STAGES = G::STAGES, QBUFS = G::QBUFS, OFF_Q = G::OFF_Q,
-                  OFF_K = G::OFF_K, OFF_V = G::OFF_V;
+                  OFF_K = G::OFF_K, OFF_V = G::OFF_V, PVR = G::PVR;
     constexpr uint32_t TM_O = G::TM_O;
     constexpr int DPL = HD / 32;  // dims per lane wherever one warp spreads a head_dim vector over its lanes
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -163,14 +187,19 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
     uint64_t* v_empty = v_full + STAGES;     // [STAGES]
     uint64_t* s_full = v_empty + STAGES;     // [NSB] S of one (tile, block) in TMEM
     uint64_t* p_full = s_full + NSB;         // [NSB] S consumed, P written over it (one arrival per softmax warp)
-    uint64_t* pv_done = p_full + NSB;        // [TILES] a P V of this tile has completed (O quiescent until the next P)
-    uint64_t* o_full = pv_done + TILES;      // [TILES] last P V of the item accumulated
+    // pv_done[t][k % PVR]: the k-th P V of tile t has completed (O quiescent until the tile's next P). A RING of barriers
+    // per tile, because a parity wait only tells "this phase or the one before": Q K^T runs up to NSB steps ahead, so
+    // when a warpgroup starts block k it knows P V(k - PVR) is complete and nothing about the ones between. With one
+    // barrier a rescale at block k could take "P V(k-3) done" for "P V(k-1) done" (found by the parity tests of the
+    // three-tile geometry: a wrong tile in items with fewer live tiles than S buffers).
+    uint64_t* pv_done = p_full + NSB;        // [TILES][PVR]
+    uint64_t* o_full = pv_done + TILES * PVR;  // [TILES] last P V of the item accumulated
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + TILES);
     float* side_f = reinterpret_cast<float*>(smem + G::OFF_SIDE);
     float* kt_ring = side_f;                  // [2][2*HD]: k then v of the lone tail key, item parity
     float* q_side = kt_ring + 2 * 2 * HD;     // [2][HD]
-    float* p_side = q_side + 2 * HD;          // [2][64]
-    float* merge = p_side + 2 * 64;           // [HD + 32]
+    float* p_side = q_side + 2 * HD;          // [2][KPW]
+    float* merge = p_side + 2 * KPW;          // [HD + 32]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -179,12 +208,13 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
     const bool tail_epi = tail_valid == 1 && n_full >= 1;
     const int n_blocks = n_full + ((tail_valid > 0 && !tail_epi) ? 1 : 0);
     const bool smode = side_mode != 0;
+    const int s_rows = S - (smode ? 1 : 0);  // query rows that tiles cover
 
-    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
-        printf("aigv attention: dynamic smem base not 1024B aligned\n");
-        __trap();
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();  // dynamic smem base must be 1024-byte aligned
+    if (warp == WARP_PRODUCER && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_kv);
     }
-    if (warp == WARP_PRODUCER && lane == 0) tma_prefetch_desc(&tm_qkv);
     if (warp == WARP_MMA) {
         if (lane == 0) {
             for (int b = 0; b < QBUFS; ++b) {
@@ -202,7 +232,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                 mbar_init(&p_full[b], 4);
             }
             for (int t = 0; t < TILES; ++t) {
-                mbar_init(&pv_done[t], 1);
+                for (int k = 0; k < PVR; ++k) mbar_init(&pv_done[t * PVR + k], 1);
                 mbar_init(&o_full[t], 1);
             }
             fence_mbar_init();
@@ -217,34 +247,33 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= SOFTMAX_WARPS) {
-        reg_dec<REGS_SERVICE>();
+        reg_dec<G::REGS_SERVICE>();
         if (warp == WARP_PRODUCER) {
             // ------------------------------------------------------------ TMA producer
             int it = 0;
+            uint32_t kst = 0, kph = 0;  // K/V ring position of the next block to load
             for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++it) {
-                const Item m = decode_item(i, n_chunks, rot_div, H, S, smode);
+                const Item m = decode_item<CHUNK, TILES>(i, n_chunks, rot_div, H, S, s_rows, smode);
                 const int qb = it % QBUFS;
                 auto load_kv = [&](int j) {
-                    const int kv = it * n_blocks + j;
-                    const int st = kv % STAGES;
-                    const uint32_t ph = (kv / STAGES) & 1;
                     const int r = m.row_base + j * BKV;
-                    mbar_wait(&k_empty[st], ph ^ 1);
+                    mbar_wait(&k_empty[kst], kph ^ 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&k_full[st], KV_BYTES);
+                        mbar_arrive_expect_tx(&k_full[kst], KV_BYTES);
                         for (int a = 0; a < ATOMS; ++a)
-                            tma_load_2d(smem + OFF_K + st * KV_BYTES + a * KV_ATOM, &tm_qkv, &k_full[st],
+                            tma_load_2d(smem + OFF_K + kst * KV_BYTES + a * KV_ATOM, &tm_kv, &k_full[kst],
                                         H * HD + m.head * HD + a * 64, r);
                     }
                     __syncwarp();
-                    mbar_wait(&v_empty[st], ph ^ 1);
+                    mbar_wait(&v_empty[kst], kph ^ 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&v_full[st], KV_BYTES);
+                        mbar_arrive_expect_tx(&v_full[kst], KV_BYTES);
                         for (int a = 0; a < ATOMS; ++a)
-                            tma_load_2d(smem + OFF_V + st * KV_BYTES + a * KV_ATOM, &tm_qkv, &v_full[st],
+                            tma_load_2d(smem + OFF_V + kst * KV_BYTES + a * KV_ATOM, &tm_kv, &v_full[kst],
                                         2 * H * HD + m.head * HD + a * 64, r);
                     }
                     __syncwarp();
+                    if (++kst == static_cast<uint32_t>(STAGES)) { kst = 0; kph ^= 1; }
                 };
                 // With a single Q buffer the Q tiles can only land after the previous item's last Q K^T: have the
                 // first K/V block in flight before waiting for that.
@@ -255,7 +284,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                     mbar_arrive_expect_tx(&q_full[qb], m.n_t * Q_BYTES);
                     for (int t = 0; t < m.n_t; ++t)
                         for (int a = 0; a < ATOMS; ++a)
-                            tma_load_2d(smem + OFF_Q + (qb * TILES + t) * Q_BYTES + a * Q_ATOM, &tm_qkv, &q_full[qb],
+                            tma_load_2d(smem + OFF_Q + (qb * TILES + t) * Q_BYTES + a * Q_ATOM, &tm_q, &q_full[qb],
                                         m.head * HD + a * 64, m.row_base + m.q0 + t * BQ);
                 }
                 __syncwarp();
@@ -284,90 +313,122 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
             const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + OFF_V), KV_ATOM, 1024);
             constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
-            struct Cur { int it, j, t, n_t; };
-            auto item_nt = [&](int it) -> int {
-                const long long i = static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x;
-                if (i >= n_items) return 0;
-                return decode_item(static_cast<int>(i), n_chunks, rot_div, H, S, smode).n_t;
+            const int my_items = (n_items > static_cast<int>(blockIdx.x))
+                                     ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                                     : 0;
+            const bool uniform_nt = (s_rows % CHUNK) == 0;  // every item has all its tiles live
+            auto nt_of = [&](int it) -> int {
+                if (uniform_nt) return TILES;
+                return decode_item<CHUNK, TILES>(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), n_chunks,
+                                                 rot_div, H, S, s_rows, smode).n_t;
             };
-            auto advance = [&](Cur& c) {
-                if (++c.t == c.n_t) {
-                    c.t = 0;
-                    if (++c.j == n_blocks) {
-                        c.j = 0;
-                        ++c.it;
-                        c.n_t = item_nt(c.it);
+            // Q K^T cursor
+            int q_it = 0, q_j = 0, q_t = 0, q_nt = my_items ? nt_of(0) : 0;
+            uint32_t q_b = 0, q_kst = 0, q_kph = 0, q_qb = 0, q_qph = 0;
+            // P V cursor
+            int p_it = 0, p_j = 0, p_t = 0, p_nt = q_nt;
+            uint32_t p_b = 0, p_bph = 0, p_vst = 0, p_vph = 0;
+            uint32_t pv_cnt[TILES];  // P V steps issued per tile: slot of the tile's pv_done ring = count % PVR
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) pv_cnt[t] = 0;
+            auto step = [&](bool do_pv, bool do_qk) {
+                if (do_pv) {
+                    mbar_wait(&p_full[p_b], p_bph);  // S consumed, P in TMEM, O rescaled if it had to be
+                    if (p_t == 0) mbar_wait(&v_full[p_vst], p_vph);
+                }
+                if (do_qk && q_t == 0) {
+                    if (q_j == 0) mbar_wait(&q_full[q_qb], q_qph);
+                    mbar_wait(&k_full[q_kst], q_kph);
+                }
+                tc_fence_after();
+                const bool p_last_t = p_t == p_nt - 1, p_last_j = p_j == n_blocks - 1;
+                const bool q_last_t = q_t == q_nt - 1, q_last_j = q_j == n_blocks - 1;
+                const uint64_t vd = v_desc0 + ((p_vst * static_cast<uint32_t>(KV_BYTES)) >> 4);
+                const uint32_t tm_p = tmem_u + p_b * BKV;  // bf16 pairs in the first BKV/2 columns of the S buffer
+                const uint32_t tm_o = tmem_u + TM_O + p_t * HD;
+                const uint64_t qd = q_desc0 + (((q_qb * TILES + q_t) * static_cast<uint32_t>(Q_BYTES)) >> 4);
+                const uint64_t kd = k_desc0 + ((q_kst * static_cast<uint32_t>(KV_BYTES)) >> 4);
+                const uint32_t tm_s = tmem_u + q_b * BKV;
+                if (AIGV_ATTN_MMA1T || elect_one()) {
+                    if (do_pv) {
+#pragma unroll
+                        for (int k = 0; k < BKV / 16; ++k)
+                            // A = P from TMEM: 8 columns (16 keys) per step; B = V rows [16k, 16k+16): 2 KiB apart
+                            umma_bf16_ts(tm_o, tm_p + k * 8, vd + ((k * 2048) >> 4), idesc_pv, (p_j | k) != 0 ? 1u : 0u);
+                        uint32_t slot = 0;
+#pragma unroll
+                        for (int t = 0; t < TILES; ++t)
+                            if (t == p_t) slot = pv_cnt[t] & (PVR - 1);
+                        umma_commit(&pv_done[p_t * PVR + slot]);
+                        if (p_last_t) umma_commit(&v_empty[p_vst]);
+                        if (p_last_j) umma_commit(&o_full[p_t]);
+                    }
+                    if (do_qk) {
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k)  // d axis: 4 steps of 32 B inside each 64-column atom
+                            umma_bf16_ss(tm_s, qd + (((k >> 2) * Q_ATOM + (k & 3) * 32) >> 4),
+                                         kd + (((k >> 2) * KV_ATOM + (k & 3) * 32) >> 4), idesc_qk, k != 0 ? 1u : 0u);
+                        umma_commit(&s_full[q_b]);
+                        if (q_last_t) {
+                            umma_commit(&k_empty[q_kst]);
+                            if (q_last_j) umma_commit(&q_empty[q_qb]);
+                        }
+                    }
+                }
+                if (!AIGV_ATTN_MMA1T) __syncwarp();
+                if (do_pv) {
+#pragma unroll
+                    for (int t = 0; t < TILES; ++t)
+                        if (t == p_t) ++pv_cnt[t];
+                    if (++p_b == static_cast<uint32_t>(NSB)) { p_b = 0; p_bph ^= 1; }
+                    if (p_last_t) {
+                        p_t = 0;
+                        if (++p_vst == static_cast<uint32_t>(STAGES)) { p_vst = 0; p_vph ^= 1; }
+                        if (p_last_j) {
+                            p_j = 0;
+                            ++p_it;
+                            p_nt = p_it < my_items ? nt_of(p_it) : 0;
+                        } else {
+                            ++p_j;
+                        }
+                    } else {
+                        ++p_t;
+                    }
+                }
+                if (do_qk) {
+                    if (++q_b == static_cast<uint32_t>(NSB)) q_b = 0;
+                    if (q_last_t) {
+                        q_t = 0;
+                        if (++q_kst == static_cast<uint32_t>(STAGES)) { q_kst = 0; q_kph ^= 1; }
+                        if (q_last_j) {
+                            q_j = 0;
+                            ++q_it;
+                            if (++q_qb == static_cast<uint32_t>(QBUFS)) { q_qb = 0; q_qph ^= 1; }
+                            q_nt = q_it < my_items ? nt_of(q_it) : 0;
+                        } else {
+                            ++q_j;
+                        }
+                    } else {
+                        ++q_t;
                     }
                 }
             };
-            Cur cq{0, 0, 0, item_nt(0)};
-            Cur cp = cq;
-            uint32_t gq = 0, gp = 0;
-            auto issue_qk = [&]() {
-                const int qb = cq.it % QBUFS;
-                const int kv = cq.it * n_blocks + cq.j;
-                const int st = kv % STAGES;
-                if (cq.j == 0 && cq.t == 0) mbar_wait(&q_full[qb], (cq.it / QBUFS) & 1);
-                if (cq.t == 0) mbar_wait(&k_full[st], (kv / STAGES) & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t qd = umma_desc_advance(q_desc0, (qb * TILES + cq.t) * Q_BYTES);
-                    const uint64_t kd = umma_desc_advance(k_desc0, st * KV_BYTES);
-                    const uint32_t b = gq % NSB;
-                    const uint32_t tm_s = tmem_u + b * BKV;
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)  // d axis: 4 steps of 32 B inside each 64-column atom
-                        umma_bf16_ss(tm_s, umma_desc_advance(qd, (k >> 2) * Q_ATOM + (k & 3) * 32),
-                                     umma_desc_advance(kd, (k >> 2) * KV_ATOM + (k & 3) * 32), idesc_qk, k != 0 ? 1u : 0u);
-                    umma_commit(&s_full[b]);
-                    if (cq.t == cq.n_t - 1) {
-                        umma_commit(&k_empty[st]);
-                        if (cq.j == n_blocks - 1) umma_commit(&q_empty[qb]);
-                    }
-                }
-                __syncwarp();
-                ++gq;
-                advance(cq);
-            };
-            auto issue_pv = [&]() {
-                const uint32_t b = gp % NSB;
-                const int kv = cp.it * n_blocks + cp.j;
-                const int st = kv % STAGES;
-                mbar_wait(&p_full[b], (gp / NSB) & 1);  // S consumed, P in TMEM, O rescaled if it had to be
-                if (cp.t == 0) mbar_wait(&v_full[st], (kv / STAGES) & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t vd = umma_desc_advance(v_desc0, st * KV_BYTES);
-                    const uint32_t tm_p = tmem_u + b * BKV;  // bf16 pairs in the first 64 columns of the S buffer
-                    const uint32_t tm_o = tmem_u + TM_O + cp.t * HD;
-#pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k)
-                        // A = P from TMEM: 8 columns (16 keys) per step; B = V rows [16k, 16k+16): 2 KiB apart
-                        umma_bf16_ts(tm_o, tm_p + k * 8, umma_desc_advance(vd, k * 2048), idesc_pv,
-                                     (cp.j | k) != 0 ? 1u : 0u);
-                    umma_commit(&pv_done[cp.t]);
-                    if (cp.t == cp.n_t - 1) umma_commit(&v_empty[st]);
-                    if (cp.j == n_blocks - 1) umma_commit(&o_full[cp.t]);
-                }
-                __syncwarp();
-                ++gp;
-                advance(cp);
-            };
-            while (gq < static_cast<uint32_t>(NSB) && cq.n_t) issue_qk();
-            while (cp.n_t) {
-                issue_pv();
-                if (cq.n_t) issue_qk();
+            if (!AIGV_ATTN_MMA1T || elect_one()) {
+                for (int pre = 0; pre < NSB && q_nt; ++pre) step(false, true);
+                while (p_nt) step(true, q_nt != 0);
             }
+            __syncwarp();
         } else {
             // ------------------------------------------------------------ the class-token query row (side warps)
             // Both warps consume every K/V stage (the ring's empty barriers expect them); on items that own the
-            // class-token row each warp runs an fp32 online softmax over its 64 keys of every block.
+            // class-token row each warp runs an fp32 online softmax over its KPW keys of every block.
+            constexpr int KPL = KPW / 32;  // keys per lane
             const int w = warp - WARP_SIDE;
             float* qs = q_side + w * HD;
-            float* ps = p_side + w * 64;
-            int it = 0;
-            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++it) {
-                const Item m = decode_item(i, n_chunks, rot_div, H, S, smode);
+            float* ps = p_side + w * KPW;
+            uint32_t kst = 0, kph = 0;
+            for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+                const Item m = decode_item<CHUNK, TILES>(i, n_chunks, rot_div, H, S, s_rows, smode);
                 float m_run = -INFINITY, l_lane = 0.f, o_acc[DPL];
 #pragma unroll
                 for (int e = 0; e < DPL; ++e) o_acc[e] = 0.f;
@@ -378,17 +439,14 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                     __syncwarp();
                 }
                 for (int j = 0; j < n_blocks; ++j) {
-                    const int kv = it * n_blocks + j;
-                    const int st = kv % STAGES;
-                    const uint32_t ph = (kv / STAGES) & 1;
-                    mbar_wait(&k_full[st], ph);
+                    mbar_wait(&k_full[kst], kph);
                     float corr = 1.f;
-                    if (m.side) {  // side mode: every block is full (S = 256 k + 1, the tail key is folded at the end)
-                        const uint8_t* kb = smem + OFF_K + st * KV_BYTES;
-                        float sc[2];
+                    if (m.side) {  // side mode: every block is full (S = 128 k + 1, the tail key is folded at the end)
+                        const uint8_t* kb = smem + OFF_K + kst * KV_BYTES;
+                        float sc[KPL];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int key = w * 64 + lane + 32 * h;
+                        for (int h = 0; h < KPL; ++h) {
+                            const int key = w * KPW + lane + 32 * h;
                             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                             for (int a = 0; a < ATOMS; ++a)
@@ -404,28 +462,34 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                                 }
                             sc[h] = a0 + a1;
                         }
-                        float mb = fmaxf(sc[0], sc[1]);
+                        float mb = sc[0];
+#pragma unroll
+                        for (int h = 1; h < KPL; ++h) mb = fmaxf(mb, sc[h]);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
                         const float m_new = fmaxf(m_run, mb);
                         corr = ex2f(m_run - m_new);
-                        const float p0 = ex2f(sc[0] - m_new), p1 = ex2f(sc[1] - m_new);
-                        l_lane = fmaf(l_lane, corr, p0 + p1);
+                        float psum = 0.f;
+#pragma unroll
+                        for (int h = 0; h < KPL; ++h) {
+                            const float pv = ex2f(sc[h] - m_new);
+                            ps[lane + 32 * h] = pv;
+                            psum += pv;
+                        }
+                        l_lane = fmaf(l_lane, corr, psum);
                         m_run = m_new;
-                        ps[lane] = p0;
-                        ps[lane + 32] = p1;
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&k_empty[st]);
-                    mbar_wait(&v_full[st], ph);
+                    if (lane == 0) mbar_arrive(&k_empty[kst]);
+                    mbar_wait(&v_full[kst], kph);
                     if (m.side) {
-                        const uint8_t* vb = smem + OFF_V + st * KV_BYTES + ((lane * DPL) >> 6) * KV_ATOM;
+                        const uint8_t* vb = smem + OFF_V + kst * KV_BYTES + ((lane * DPL) >> 6) * KV_ATOM;
                         const int boff = ((lane * DPL) & 63) * 2;  // byte offset of this lane's dims inside the 128-byte row
 #pragma unroll
                         for (int e = 0; e < DPL; ++e) o_acc[e] *= corr;
 #pragma unroll 4
-                        for (int kk = 0; kk < 64; ++kk) {
-                            const int key = w * 64 + kk;
+                        for (int kk = 0; kk < KPW; ++kk) {
+                            const int key = w * KPW + kk;
                             const float pk = ps[kk];
                             const uint8_t* vr = vb + key * 128 + ((((boff >> 4) ^ (key & 7)) << 4) | (boff & 15));
 #pragma unroll
@@ -437,7 +501,8 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                         }
                     }
                     __syncwarp();  // ps is rewritten by the next block; all lanes are done with the V stage
-                    if (lane == 0) mbar_arrive(&v_empty[st]);
+                    if (lane == 0) mbar_arrive(&v_empty[kst]);
+                    if (++kst == static_cast<uint32_t>(STAGES)) { kst = 0; kph ^= 1; }
                 }
                 if (m.side) {
                     float l = l_lane;
@@ -484,71 +549,69 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
         }
     } else {
         // ------------------------------------------------------------ softmax warpgroups: one query row per thread
-        reg_inc<REGS_SOFTMAX>();
+        reg_inc<G::REGS_SOFTMAX>();
         const int t = warp >> 2;                      // query tile of this warpgroup
         const int wq = warp & 3;                      // TMEM lane quadrant
         const int r = wq * 32 + lane;                 // row within the tile == TMEM lane
-        // Ping-pong (measured: without it the two softmax warps that share an SM sub-partition drift into lock step,
-        // both in their MUFU-heavy phase at once and both out of it at once: XU 66% busy). Warps w (tile 0) and w + 4
-        // (tile 1) sit on the same scheduler; named barrier 2 + 2*wq + t is "tile t's turn" of that pair: a warp waits
-        // for its turn before its exponentials and hands the turn over right after them, so one warp's tcgen05.ld /
-        // row max / tcgen05.st / barrier traffic runs under the other's exponentials. Tile 0 goes first.
-        const uint32_t pp_mine = 2 + 2 * wq + t, pp_other = 2 + 2 * wq + (t ^ 1);
-        if (AIGV_ATTN_PINGPONG && t == 1) named_bar_arrive(pp_other, 64);
+        // Exponential turns: warps wq, wq + 4, ... (tiles 0, 1, ...) sit on the same scheduler; named barrier
+        // 2 + TILES*wq + t is "tile t's turn" of that group. A warp waits for its turn before its exponentials and hands
+        // the turn to the next tile right after them. Tile 0 goes first.
+        const uint32_t pp_mine = 2 + TILES * wq + t, pp_next = 2 + TILES * wq + (t + 1 == TILES ? 0 : t + 1);
+        if (AIGV_ATTN_PINGPONG && t == TILES - 1) named_bar_arrive(pp_next, 64);
         const uint32_t tm_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
         const uint32_t tm_o = tm_lane + TM_O + t * HD;
-        uint32_t g_base = 0;     // (tile, block) steps of all earlier items
-        uint32_t n_pv = 0;       // P V steps of this tile so far (phase of pv_done)
-        uint32_t n_items_t = 0;  // items this tile took part in (phase of o_full)
+        uint32_t sb = 0, sph = 0;  // S buffer / parity of this tile's next step; advanced by n_t per block
+        uint32_t n_pv = 0;         // P V steps of this tile so far (phase of pv_done)
+        uint32_t n_items_t = 0;    // items this tile took part in (phase of o_full)
         int it = 0;
+        auto advance_sb = [&](uint32_t steps) {
+            sb += steps;
+            while (sb >= static_cast<uint32_t>(NSB)) { sb -= NSB; sph ^= 1; }
+        };
+        advance_sb(t);  // tile t's first step is step t of the sequence (when all tiles are live; see below)
         for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++it) {
-            const Item m = decode_item(i, n_chunks, rot_div, H, S, smode);
+            const Item m = decode_item<CHUNK, TILES>(i, n_chunks, rot_div, H, S, s_rows, smode);
             const int qb = it % QBUFS;
             const uint32_t qph = (it / QBUFS) & 1;
+            // Step index of (block j, tile t) inside this item is j * n_t + t: sb/sph were positioned for tile t with all
+            // TILES live (offset t from the item's first step); with fewer live tiles the offset is the same t (t < n_t).
             if (t >= m.n_t) {  // this warpgroup's tile holds no query row: only release Q (and keep passing the turn)
                 mbar_wait(&q_full[qb], qph);
                 if (lane == 0) mbar_arrive(&q_empty[qb]);
-                g_base += n_blocks * m.n_t;
+                advance_sb(static_cast<uint32_t>(n_blocks * m.n_t));
                 if (AIGV_ATTN_PINGPONG)
                     for (int j = 0; j < n_blocks; ++j) {
                         named_bar_sync(pp_mine, 64);
-                        named_bar_arrive(pp_other, 64);
+                        named_bar_arrive(pp_next, 64);
                     }
                 continue;
             }
             const int tile_q0 = m.q0 + t * BQ;
             // Warps whose 32 query rows are all beyond the sequence skip the softmax math; they still take part in
             // the barrier protocol so the MMA warp's schedule is unchanged.
-            const bool warp_live = tile_q0 + wq * 32 < S;
+            const bool warp_live = tile_q0 + wq * 32 < s_rows;
             float m_ref = -INFINITY;  // reference maximum, already multiplied by scale*log2e
             float l_run = 0.f;
             float s_t = 0.f;          // the lone tail key's score (log2 units)
 
             for (int j = 0; j < n_blocks; ++j) {
-                const uint32_t g = g_base + j * m.n_t + t;
-                const uint32_t b = g % NSB;
+                const uint32_t b = sb;
                 const uint32_t tm_s = tm_lane + b * BKV;
-                mbar_wait(&s_full[b], (g / NSB) & 1);
+                mbar_wait(&s_full[b], sph);
                 tc_fence_after();
                 if (warp_live) {
                     uint32_t v[BKV];
-                    if (AIGV_ATTN_ABL & 2) {
 #pragma unroll
-                        for (int c = 0; c < BKV; ++c) v[c] = __float_as_uint(-0.01f * (c + j) - l_run * 1e-30f);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(tm_s + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
-                        tmem_ld_wait();
-                    }
+                    for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(tm_s + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+                    tmem_ld_wait();
                     if (j >= n_full) {  // masked tail block (never taken for ViT sequences)
 #pragma unroll
                         for (int c = 0; c < BKV; ++c)
                             if (c >= tail_valid) v[c] = 0xff800000u;
                     }
                     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-                    if (AIGV_ATTN_ABL & 8) mx0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[77]));
 #pragma unroll
-                    for (int c = 0; c < ((AIGV_ATTN_ABL & 8) ? 0 : BKV); c += 8) {
+                    for (int c = 0; c < BKV; c += 8) {
                         mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[c]), __uint_as_float(v[c + 1])));
                         mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])));
                         mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])));
@@ -559,12 +622,10 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                     if (__any_sync(0xffffffffu, need)) {                 // warp-uniform: TMEM ops are warp-collective
                         const float new_ref = need ? mxs : m_ref;
                         if (j > 0) {
-                            // O must be quiescent: wait for this tile's previous P V (with two S buffers s_full already
-                            // implies it), then rescale O in place
-                            if (NSB > 2) {
-                                mbar_wait(&pv_done[t], (n_pv - 1) & 1);
-                                tc_fence_after();
-                            }
+                            // O must be quiescent: wait for this tile's previous P V (ring slot (n_pv-1) % PVR, use
+                            // (n_pv-1) / PVR of that slot), then rescale O in place
+                            mbar_wait(&pv_done[t * PVR + ((n_pv - 1) & (PVR - 1))], ((n_pv - 1) / PVR) & 1);
+                            tc_fence_after();
                             const float alpha = ex2f(m_ref - new_ref);  // 1 for rows that keep their reference
 #pragma unroll 1
                             for (int c = 0; c < HD; c += 32) {
@@ -597,13 +658,8 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                                 } else {
                                     float x0, x1;
                                     unpack2(x, x0, x1);
-                                    if (AIGV_ATTN_ABL & 1) {
-                                        p[2 * q] = x0;
-                                        p[2 * q + 1] = x1;
-                                    } else {
-                                        p[2 * q] = ex2f(x0);
-                                        p[2 * q + 1] = ex2f(x1);
-                                    }
+                                    p[2 * q] = ex2f(x0);
+                                    p[2 * q + 1] = ex2f(x1);
                                 }
                             }
                             sum01 = add2(sum01, add2(pack2(p[0], p[1]), pack2(p[4], p[5])));
@@ -611,14 +667,9 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
 #pragma unroll
                             for (int q = 0; q < 4; ++q) pk[(e >> 1) + q] = pack_bf16x2(p[2 * q], p[2 * q + 1]);
                         }
-                        if (AIGV_ATTN_ABL & 4) {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) l_run += __uint_as_float(pk[e]) * 1e-30f;
-                        } else {
-                            tmem_st_32x16(tm_s + (c >> 1), pk);
-                        }
+                        tmem_st_32x16(tm_s + (c >> 1), pk);  // P over S columns this thread has already consumed
                     }
-                    if (AIGV_ATTN_PINGPONG) named_bar_arrive(pp_other, 64);
+                    if (AIGV_ATTN_PINGPONG) named_bar_arrive(pp_next, 64);
                     tmem_st_wait();
                     float s0, s1, s2, s3;
                     unpack2(sum01, s0, s1);
@@ -626,12 +677,13 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                     l_run += (s0 + s1) + (s2 + s3);
                 } else if (AIGV_ATTN_PINGPONG) {
                     named_bar_sync(pp_mine, 64);
-                    named_bar_arrive(pp_other, 64);
+                    named_bar_arrive(pp_next, 64);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[b]);  // one arrival per softmax warp
                 ++n_pv;
+                advance_sb(static_cast<uint32_t>(m.n_t));
                 if (j == 0) {
                     // The lone tail key's score from this row's Q line in shared memory (the producer's fp32 copy of
                     // the key is covered by q_full), then this warp is done with the Q buffer.
@@ -658,7 +710,6 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                     if (lane == 0) mbar_arrive(&q_empty[qb]);
                 }
             }
-            g_base += n_blocks * m.n_t;
 
             // epilogue: fold the lone tail key in (exact reference update), normalise, store
             float alpha = 1.f, p_t = 0.f;
@@ -682,7 +733,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
                     uint32_t v[32];
                     tmem_ld_32x32(tm_o + c, v);
                     tmem_ld_wait();
-                    if (q < S) {
+                    if (q < s_rows) {
 #pragma unroll
                         for (int e = 0; e < 32; e += 8) {
                             float y[8];
@@ -726,15 +777,17 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __nv_bfl
 }
 
 template <int HD>
-cudaError_t launch_attention2_hd(const CUtensorMap& tm_qkv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames,
-                                 int S, int heads, float softmax_scale, int num_sms, cudaStream_t stream) {
+cudaError_t launch_attention2_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const __nv_bfloat16* qkv,
+                                 __nv_bfloat16* out, int frames, int S, int heads, float softmax_scale, int num_sms,
+                                 cudaStream_t stream) {
+    using G = Geo2<HD>;
     static unsigned long long optin_mask = 0;
-    cudaError_t e = ensure_smem_optin(reinterpret_cast<const void*>(&attention_fwd2_kernel<HD>), Geo2<HD>::SMEM_BYTES,
-                                      optin_mask);
+    cudaError_t e = ensure_smem_optin(reinterpret_cast<const void*>(&attention_fwd2_kernel<HD>), G::SMEM_BYTES, optin_mask);
     if (e != cudaSuccess) return e;
-    // side mode: S = k * 256 + 1 (k >= 1) -- the leftover query row rides on the side warps of chunk 0
-    const int side_mode = (S > CHUNK && S % CHUNK == 1 && qkv != nullptr) ? 1 : 0;
-    const int n_chunks = side_mode ? S / CHUNK : (S + CHUNK - 1) / CHUNK;
+    // side mode: S = k * 128 + 1 (k >= 1) -- the leftover query row rides on the side warps of the first chunk
+    const int side_mode = (S > BQ && S % BQ == 1 && qkv != nullptr) ? 1 : 0;
+    const int s_rows = S - side_mode;
+    const int n_chunks = (s_rows + G::CHUNK - 1) / G::CHUNK;
     const long long n_items = static_cast<long long>(frames) * heads * n_chunks;
     if (n_items > 0x3fffffff) return cudaErrorInvalidValue;
     int grid = num_sms > 0 ? num_sms : 148;
@@ -742,8 +795,8 @@ cudaError_t launch_attention2_hd(const CUtensorMap& tm_qkv, const __nv_bfloat16*
     int rot_div = grid / n_chunks;
     if (rot_div < 1) rot_div = 1;
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    attention_fwd2_kernel<HD><<<grid, THREADS, Geo2<HD>::SMEM_BYTES, stream>>>(
-        tm_qkv, qkv, out, S, heads, static_cast<int>(n_items), n_chunks, rot_div, side_mode, scale_log2);
+    attention_fwd2_kernel<HD><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(
+        tm_q, tm_kv, qkv, out, S, heads, static_cast<int>(n_items), n_chunks, rot_div, side_mode, scale_log2);
     return cudaGetLastError();
 }
 
@@ -765,13 +818,15 @@ cudaError_t launch_exp2_poly_test(const float* x, float* y, int n, cudaStream_t 
     return cudaGetLastError();
 }
 
-int attention2_box_rows() { return BQ; }  // Q, K and V tiles are all [128 rows x 64 columns] boxes of the qkv matrix
+int attention2_q_box_rows() { return BQ; }
+int attention2_kv_box_rows(int head_dim) { return head_dim == 64 ? Geo2<64>::BKV : Geo2<128>::BKV; }
 
-cudaError_t launch_attention2(const CUtensorMap& tm_qkv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S,
-                              int heads, int head_dim, float softmax_scale, int num_sms, cudaStream_t stream) {
+cudaError_t launch_attention2(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const __nv_bfloat16* qkv,
+                              __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
+                              int num_sms, cudaStream_t stream) {
     if (frames <= 0 || S <= 0 || heads <= 0) return cudaErrorInvalidValue;
-    if (head_dim == 64) return launch_attention2_hd<64>(tm_qkv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream);
-    if (head_dim == 128) return launch_attention2_hd<128>(tm_qkv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream);
+    if (head_dim == 64) return launch_attention2_hd<64>(tm_q, tm_kv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream);
+    if (head_dim == 128) return launch_attention2_hd<128>(tm_q, tm_kv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream);
     return cudaErrorInvalidValue;
 }
 

@@ -241,9 +241,26 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (lane == 0) tma_store_wait_read<0>();  // staging tiles of the previous output tile have been read out
                 __syncwarp();
                 issue_xload(0);
-                if (kResid == 2 && row0 + lane < M && colb < N)  // the later chunks are fetched serially: have them in L2
-                    prefetch_l2_bulk(ep.resid_in + static_cast<size_t>(row0 + lane) * N + colb,
-                                     4u * static_cast<uint32_t>(N - colb < SLICE_COLS ? N - colb : SLICE_COLS));
+                // x_old is streamed from HBM (the residual stream is 4 B x M x N, far beyond L2): pull this warp's rows of
+                // the NEXT tile into L2 now, a whole mainloop ahead of the TMA fetches that will want them (and the
+                // current tile's rows for the first tile of this CTA pair).
+                auto prefetch_rows = [&](int tl) {
+                    const int mb = tl / num_n, nb = tl % num_n;
+                    const int r0 = mb * 2 * BM + static_cast<int>(rank) * BM + quad * 32 + lane;
+                    const int c0 = nb * BN + slice * SLICE_COLS;
+                    if (r0 < M && c0 < N)
+                        prefetch_l2_bulk(ep.resid_in + static_cast<size_t>(r0) * N + c0,
+                                         4u * static_cast<uint32_t>(N - c0 < SLICE_COLS ? N - c0 : SLICE_COLS));
+                };
+#ifndef AIGV_GEMM_PREFETCH_NEXT
+#define AIGV_GEMM_PREFETCH_NEXT 1
+#endif
+                if (AIGV_GEMM_PREFETCH_NEXT) {
+                    if (tile == pair) prefetch_rows(tile);
+                    if (tile + num_pairs < num_tiles) prefetch_rows(tile + num_pairs);
+                } else if (kResid == 2) {
+                    prefetch_rows(tile);
+                }
             }
             // LayerNorm-fused consumer: this thread's row statistics (fetched ahead of the accumulator wait)
             float mean = 0.f, rstd = 1.f;

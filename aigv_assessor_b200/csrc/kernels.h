@@ -64,11 +64,14 @@ cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, 
                              const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads, int head_dim,
                              float softmax_scale, cudaStream_t stream);
 
-// Round-2 persistent kernel (attention2_tcgen05.cu): ONE map over the qkv matrix with a [attention2_box_rows(), 64] box
-// serves Q, K and V; any sequence length; head_dim 64 or 128; num_sms = persistent CTAs to launch.
-int attention2_box_rows();
-cudaError_t launch_attention2(const CUtensorMap& tm_qkv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S,
-                              int heads, int head_dim, float softmax_scale, int num_sms, cudaStream_t stream);
+// Round-2 persistent kernel (attention2_tcgen05.cu): two maps over the qkv matrix, boxes [attention2_q_box_rows(), 64] (Q
+// tiles) and [attention2_kv_box_rows(head_dim), 64] (K / V blocks); any sequence length; head_dim 64 or 128; num_sms =
+// persistent CTAs to launch.
+int attention2_q_box_rows();
+int attention2_kv_box_rows(int head_dim);
+cudaError_t launch_attention2(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const __nv_bfloat16* qkv,
+                              __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
+                              int num_sms, cudaStream_t stream);
 
 // Test hook: y[i] = the attention kernel's FMA-pipe 2^x (exp2_poly2) for x[i] (softmax arguments are <= 8).
 cudaError_t launch_exp2_poly_test(const float* x, float* y, int n, cudaStream_t stream);
@@ -125,6 +128,7 @@ namespace aigv {
 int plan_axis(int in_size, int out_size, std::vector<int32_t>& kk, std::vector<int32_t>& bounds);
 int plan_max_rows(const std::vector<int32_t>& by, int out_h);
 int plan_max_span_bytes(const std::vector<int32_t>& bx, int out_w);
+bool preprocess_fits(int max_rows, int span_bytes);  // does the source window of a 32x32 output block fit in shared memory?
 cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
                                    int64_t row_stride, const ResizePlan& plan, int max_rows, int span_bytes,
                                    const float* lut, int tile, int tiles_x, int tiles_per_frame, int tile_offset,

@@ -212,6 +212,10 @@ int plan_max_span_bytes(const std::vector<int32_t>& bx, int out_w) {
     return best + 4;
 }
 
+bool preprocess_fits(int max_rows, int span_bytes) {
+    return static_cast<size_t>(max_rows) * (TX * 3 + span_bytes) <= 200 * 1024;
+}
+
 cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
                                    int64_t row_stride, const ResizePlan& plan, int max_rows, int span_bytes,
                                    const float* lut, int tile, int tiles_x, int tiles_per_frame, int tile_offset,

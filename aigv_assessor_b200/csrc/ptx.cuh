@@ -54,14 +54,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef AIGV_WATCHDOG_CYCLES
 #define AIGV_WATCHDOG_CYCLES (4000000000ll)
 #endif
+// The slow path is a bare spin with a cycle watchdog that traps (build with -DAIGV_WATCHDOG_PRINTF to also print which
+// barrier hung: the vprintf call sequence inlined into every wait was most of the code of the single-warp roles and
+// pushed the attention kernel's hot loops out of the instruction caches -- stall_no_inst on the MMA issuer).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {  // try_wait suspends in hardware for a bounded time per call
         if ((++spins & 0xFFFu) == 0 && clock64() - t0 > AIGV_WATCHDOG_CYCLES) {
+#ifdef AIGV_WATCHDOG_PRINTF
             printf("aigv: mbarrier watchdog block (%d,%d,%d) thread %d bar %u parity %u\n", blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#endif
             __trap();
         }
     }

@@ -102,7 +102,11 @@ class VisionEngine:
         _lib.check(st, self._h, f"aigv_set_weight({name})")
 
     def load_state_dict(self, sd: Mapping[str, object]):
-        """sd uses the reference's names: 'vision_model.*' and 'mlp1.*' (other keys are ignored)."""
+        """sd uses the reference's names: 'vision_model.*' and 'mlp1.*' (other keys are ignored). LoRA pairs of a
+        peft-wrapped tower ('...base_layer.weight' + 'lora_A/lora_B.default.weight') are merged first."""
+        if any(".lora_A." in k for k in sd):
+            sd = merge_lora_names({k: (torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v)
+                                   for k, v in sd.items()})
         for k, v in sd.items():
             if k.startswith("vision_model.") or k.startswith("mlp1."):
                 self.set_weight(k, v)
@@ -110,6 +114,11 @@ class VisionEngine:
             _lib.check(self.lib.aigv_finalize_weights(self._h, None), self._h, "aigv_finalize_weights")
         self._finalized = True
         return self
+
+    def load_checkpoint(self, path: str) -> "VisionEngine":
+        """Ingest vision_model.* / mlp1.* from a safetensors file or checkpoint directory (checkpoint.py)."""
+        from . import checkpoint
+        return self.load_state_dict(checkpoint.load_checkpoint_dir(path))
 
     @classmethod
     def from_model(cls, model, max_tiles: int = 64, llm_hidden: int | None = None) -> "VisionEngine":

@@ -87,6 +87,26 @@ def make_weights(cfg: VisionPathConfig, seed: int = 0) -> dict[str, np.ndarray]:
     return sd
 
 
+def make_stress_weights(cfg: VisionPathConfig, seed: int = 0) -> dict[str, np.ndarray]:
+    """make_weights pushed towards what TRAINED towers look like, for the pieces whose numerics differ there: qkv weights
+    x4 (peaked attention rows: the stale-max softmax and its rescale path), a few outlier channels of +-300 in the
+    position embedding (massive activations: the E[x^2] - mean^2 LayerNorm statistics of the fused epilogues), layer
+    scales spread over 0.1 .. 1."""
+    sd = make_weights(cfg, seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 7919))
+    D = cfg.hidden_size
+    pos = sd["vision_model.embeddings.position_embedding"].copy()
+    for ch, val in ((5 % D, 300.0), (33 % D, -300.0), (77 % D, 200.0)):
+        pos[..., ch] += np.float32(val)
+    sd["vision_model.embeddings.position_embedding"] = bf16_round(pos)
+    for i in range(cfg.num_layers):
+        lp = f"vision_model.encoder.layers.{i}."
+        sd[lp + "attn.qkv.weight"] = bf16_round(sd[lp + "attn.qkv.weight"] * np.float32(4.0))
+        for ls in ("ls1", "ls2"):
+            sd[lp + ls] = bf16_round(rng.uniform(0.1, 1.0, size=(D,)).astype(np.float32))
+    return sd
+
+
 def make_frames(n: int, height: int, width: int, seed: int = 1, kind: str = "smooth") -> np.ndarray:
     """uint8 HWC frames [n,H,W,3] (decord layout, /root/reference/internvl/train/internvl/eval/stage1_eval.py:452).
 
@@ -150,7 +170,7 @@ def head_weight_spec(llm: dict = HEAD_LLM):
     yield lm + "tok_embeddings.weight", (V, H), ("normal", 0.5, 0.0)
     for i in range(llm["num_hidden_layers"]):
         lp = f"{lm}layers.{i}."
-        yield lp + "attention.wqkv.weight", (qkv, H), ("uniform", H / 16.0)   # gain 4: peaked (not flat) attention, so score1 is sensitive to the visual tokens
+        yield lp + "attention.wqkv.weight", (qkv, H), ("uniform", H / 8.0)   # gain 2.8: attention that is not flat, so score1 responds to the visual tokens
         yield lp + "attention.wo.weight", (H, H), ("uniform", H)
         yield lp + "feed_forward.w1.weight", (I, H), ("uniform", H)
         yield lp + "feed_forward.w3.weight", (I, H), ("uniform", H)

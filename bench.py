@@ -111,6 +111,68 @@ def cpu_oracle_fps(cfg, sd, frames, repeats=1):
     return frames / best, best
 
 
+def reference_gpu_stack(cfg, sd, frames, dev, iters=10):
+    """COMPARATOR, never the product path: the kernel stack the unmodified reference runs on this same GPU -- cuBLASLt
+    bf16 GEMMs behind nn.Linear (modeling_intern_vit.py:129,141,189,190), the flash-attn wheel's sm_100 cubin behind
+    flash_attn_varlen_qkvpacked_func (flash_attention.py:52-55) and ATen elementwise kernels -- timed per op at this
+    bench's shapes and as the whole eager bf16 extract_feature path (the torch restatement of the reference's modules,
+    oracle/vit_oracle_torch.py, on CUDA with FA2). SURVEY.md section 8(d) "beat this" row."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import vit_oracle_torch as vt
+    res = {}
+    S, D, I, H, hd, L = cfg.tokens, cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.head_dim, cfg.num_layers
+    M = frames * S
+
+    def timeit(fn, n=iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    g = torch.Generator(device="cpu").manual_seed(7)
+    for name, N, K in (("qkv", 3 * D, D), ("proj", D, D), ("fc1", I, D), ("fc2", D, I)):
+        a = torch.randn((M, K), generator=g).to(dev, torch.bfloat16)
+        w = (torch.randn((N, K), generator=g) * K ** -0.5).to(dev, torch.bfloat16)
+        bias = torch.randn(N, generator=g).to(dev, torch.bfloat16)
+        ms = timeit(lambda: F.linear(a, w, bias))
+        res[f"gemm_{name}_ms_per_step"] = ms * L
+        res[f"gemm_{name}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        del a, w, bias
+    try:
+        from flash_attn import flash_attn_varlen_qkvpacked_func
+        qkv = torch.randn((M, 3, H, hd), generator=g).to(dev, torch.bfloat16)
+        cu = torch.arange(0, (frames + 1) * S, step=S, dtype=torch.int32, device=dev)
+        ms = timeit(lambda: flash_attn_varlen_qkvpacked_func(qkv, cu, S, 0.0, softmax_scale=None, causal=False))
+        res["attention_ms_per_step"] = ms * L
+        res["attention_tflops"] = 4.0 * frames * S * S * D / ms / 1e9
+        res["attention_kernel"] = "flash_attn_varlen_qkvpacked_func (flash-attn wheel, sm_100 cubin: mma.sync + cp.async)"
+        del qkv
+        have_fa = True
+    except Exception as e:  # pragma: no cover
+        res["attention_unavailable"] = repr(e)[:200]
+        have_fa = False
+    # whole path, eager bf16 (+FA2): the reference's own GPU configuration (stage2_eval.py:932, use_flash_attn=True)
+    tsd = {k: torch.from_numpy(v).to(dev, torch.bfloat16) for k, v in sd.items()}
+    if have_fa:
+        tsd["__use_flash_attn__"] = torch.ones(1)
+    from aigv_assessor_b200 import synth
+    pv = torch.from_numpy(synth.make_pixel_values(8, cfg, seed=99)).to(dev, torch.bfloat16).repeat(frames // 8, 1, 1, 1)
+    ms = timeit(lambda: vt.extract_feature(pv, tsd, cfg), n=3)
+    res["eager_bf16_ms_per_step"] = ms
+    res["eager_bf16_frames_per_s"] = frames / ms * 1e3
+    res["eager_attention"] = "flash-attn 2" if have_fa else "naive softmax (flash-attn unavailable)"
+    res["note"] = ("library kernels of the reference's own GPU path on this GPU (cuBLASLt, flash-attn wheel, ATen), timed "
+                   "alone per op at M = %d rows and as the eager bf16 path over %d frames; a comparator, not used by the product" % (M, frames))
+    return res
+
+
 def run_reference(args, rank, world, out):
     """CPU arm: the oracle port of the reference's path, all host threads, bounded sample per step."""
     if rank != 0:
@@ -145,6 +207,27 @@ def run_reference(args, rank, world, out):
         "gpu_launches": 0,
     }
     out.emit(json.dumps(line))
+
+
+def build_6b_engine(dev, frames):
+    """Config 5: InternViT-6B (D=3200, 25 heads x 128, I=12800, 48 layers, RMSNorm + q/k RMSNorm) + mlp1 -> 6144 with
+    random-init weights generated ON the device from synth.weight_spec (5.9 G parameters)."""
+    import torch
+    from aigv_assessor_b200 import synth
+    from aigv_assessor_b200.config import internvit_6b
+    from aigv_assessor_b200.engine import VisionEngine
+    cfg = internvit_6b()
+    eng = VisionEngine(cfg, max_tiles=frames, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    for name, shape, dist_ in synth.weight_spec(cfg):
+        if dist_[0] == "uniform":
+            t = (torch.rand(shape, generator=g, device=dev) * 2 - 1) * dist_[1] ** -0.5
+        else:
+            t = dist_[2] + dist_[1] * torch.randn(shape, generator=g, device=dev)
+        eng.set_weight(name, t.to(torch.bfloat16))
+        del t
+    eng.load_state_dict({})  # finalize
+    return cfg, eng
 
 
 def run_native(args, rank, local_rank, world, out):
@@ -184,21 +267,33 @@ def run_native(args, rank, local_rank, world, out):
     out_host = torch.empty((frames, cfg.out_tokens, cfg.llm_hidden), dtype=torch.bfloat16).pin_memory()
     n_clips = frames // clip
 
-    def step(pv, out=None):
-        out = eng.extract_feature(pv, out=out)
-        if world > 1:  # the path's only exchange: all-gather per-clip pooled features
-            pooled = out.view(n_clips, -1, cfg.llm_hidden).float().mean(1)
-            gathered = torch.empty((world * n_clips, cfg.llm_hidden), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(gathered, pooled)
-        return out
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(devs[i % R])
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    gathered = None
+    if world > 1:
+        gathered = torch.empty((world * frames, cfg.out_tokens, cfg.llm_hidden), dtype=torch.bfloat16, device=dev)
+
+    def timed_steps(n, batches, e=eng):
+        """n passes of the hot path; clips are sharded over the ranks with NO data-path collective, and the path's only
+        exchange -- one all-gather of this rank's per-clip visual tokens -- happens once, at the end."""
+        o = None
+        for i in range(n):
+            o = e.extract_feature(batches[i % len(batches)])
+        if world > 1 and o is not None and o.shape[0] == frames:
+            dist.all_gather_into_tensor(gathered, o)
+        return o
+
+    timed_steps(args.warmup, devs)
     barrier()
 
     # ---- timed region: device-resident inputs, per-kernel CUDA events on the launching stream -------------------
@@ -210,25 +305,28 @@ def run_native(args, rank, local_rank, world, out):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        step(devs[i % R])
+    timed_steps(args.steps, devs)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms_local = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = eng.launch_count - l0
     prof = eng.profile_read(reset=True)
     eng.profile(False)
 
-    # ---- e2e: host buffers, H2D + D2H inside the timed region ----------------------------------------------------
+    # ---- e2e: uint8 video frames in pinned HOST memory -> front end -> extract_feature -> visual tokens on the HOST ----
     # The public API runs on the caller's stream, so a caller pipelines exactly like this: a copy-in stream, the
-    # compute stream and a copy-out stream, double buffered, chained with events. Every step still moves its own
-    # pixel_values host->device and its visual tokens device->host inside the timed region.
-    ms_e2e = float("nan")
+    # compute stream and a copy-out stream, double buffered, chained with events. Every step moves its own frames
+    # host->device and its visual tokens device->host inside the timed region, and runs the frame front end.
+    fh, fw = 720, 1280
+    ms_e2e_local = float("nan")
+    h2d_bytes = frames * fh * fw * 3
     if not args.no_e2e:
+        gf = torch.Generator().manual_seed(77 + rank)
+        host_u8 = [torch.randint(0, 256, (frames, fh, fw, 3), generator=gf, dtype=torch.uint8).pin_memory() for _ in range(2)]
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         s_cmp = torch.cuda.current_stream()
-        stage = [torch.empty_like(devs[0]) for _ in range(2)]
+        stage = [torch.empty((frames, fh, fw, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
         outs = [torch.empty((frames, cfg.out_tokens, cfg.llm_hidden), dtype=torch.bfloat16, device=dev)
                 for _ in range(2)]
         ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -244,11 +342,12 @@ def run_native(args, rank, local_rank, world, out):
                 b = i & 1
                 with torch.cuda.stream(s_in):
                     s_in.wait_event(ev_free[b])          # stage[b] no longer read by step i-2
-                    stage[b].copy_(host[i % R], non_blocking=True)
+                    stage[b].copy_(host_u8[i & 1], non_blocking=True)
                     ev_in[b].record(s_in)
                 s_cmp.wait_event(ev_in[b])
                 s_cmp.wait_event(ev_copied[b])           # outs[b] of step i-2 has left the device
-                step(stage[b], out=outs[b])
+                pvb, _ = eng.preprocess_frames(stage[b], max_num=1)   # resize + normalise + bf16 on the device
+                eng.extract_feature(pvb, out=outs[b])
                 ev_free[b].record(s_cmp)
                 ev_out[b].record(s_cmp)
                 with torch.cuda.stream(s_out):
@@ -264,12 +363,46 @@ def run_native(args, rank, local_rank, world, out):
         e2e_run(args.steps)
         f1.record()
         barrier()
-        ms_e2e = f0.elapsed_time(f1)
+        ms_e2e_local = f0.elapsed_time(f1)
+        del stage, outs, host_u8
+
+    def timed(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / n)
+
+    extra = {}
+    # ---- config 3 shape: 32 frames (4 clips) per GPU per step --------------------------------------------------------
+    if not args.no_extra and frames >= 32:
+        half = [d[:32] for d in devs]
+        timed_steps(2, half)
+        ms32 = timed(lambda: timed_steps(1, half), 8)
+        extra["config3_32_frames_per_gpu"] = {"frames_per_s": world * 32 / ms32 * 1e3, "ms_per_step": ms32,
+                                              "note": "BASELINE config 3 shape: 32 clips per step over 8 GPUs = 4 clips (32 tiles, M = 32800) per GPU"}
+    # ---- config 4: frames -> tiles -> tokens incl. the GPU front end, 16/32/64 frames x 1/3/7 tiles per frame -------
+    if not args.no_extra:
+        sweep = []
+        for (sh, sw, mx, tiles) in ((720, 1280, 1, 1), (720, 1280, 6, 3), (512, 768, 6, 7)):
+            for nf in (16, 32, 64):
+                u8 = torch.randint(0, 256, (nf, sh, sw, 3), dtype=torch.uint8, device=dev)
+                eng.encode_frames(u8, max_num=mx)
+                ms_c = timed(lambda: eng.encode_frames(u8, max_num=mx), 2)
+                sweep.append({"frames_per_clip": nf, "tiles_per_frame": tiles, "source": f"{sw}x{sh}",
+                              "tiles_per_s": world * nf * tiles / ms_c * 1e3, "clips_per_s": world / ms_c * 1e3,
+                              "ms_per_clip": ms_c})
+                del u8
+        extra["config4_sweep"] = {"rows": sweep, "note": "uint8 frames resident on the device -> dynamic tiling front end (max_num = 1 / 6 incl. "
+                                  "thumbnail) -> extract_feature, micro-batched at %d tiles; one clip per GPU per pass" % eng.max_tiles}
 
     # ---- HBM-bound kernels of the path: achieved GB/s against the measured copy bandwidth ---------------------------
     bw = {}
     if rank == 0:
-        fh, fw, nf = 720, 1280, frames
+        nf = frames
         u8 = torch.randint(0, 256, (nf, fh, fw, 3), dtype=torch.uint8, device=dev)   # 177 MB > L2
         for _ in range(2):
             eng.preprocess_frames(u8, max_num=1)
@@ -294,10 +427,41 @@ def run_native(args, rank, local_rank, world, out):
             bw["pixel_shuffle_ln"] = {"GBps": b * prof["pixel_shuffle_ln"][1] / prof["pixel_shuffle_ln"][0] / 1e6,
                                       "bytes_per_launch": b}
 
+    # ---- config 5: InternViT-6B replicas (one per GPU) ----------------------------------------------------------------
+    if not args.no_extra and not args.no_6b:
+        try:
+            f6 = 16
+            del devs
+            torch.cuda.empty_cache()
+            cfg6, eng6 = build_6b_engine(dev, f6)
+            pv6 = torch.randn((f6, 3, cfg6.image_size, cfg6.image_size), device=dev).to(torch.bfloat16)
+            for _ in range(2):
+                o6 = eng6.extract_feature(pv6)
+            eng6.profile(True)
+            eng6.profile_read(reset=True)
+            ms6 = timed(lambda: eng6.extract_feature(pv6), 3)
+            prof6 = eng6.profile_read(reset=True)
+            tf6 = cfg6.flops_per_frame() * f6 / ms6 / 1e9
+            extra["config5_internvit_6b"] = {
+                "frames_per_s": world * f6 / ms6 * 1e3, "ms_per_step": ms6, "frames_per_step_per_gpu": f6,
+                "tflops_per_gpu": tf6, "frac_of_sustained_peak": tf6 / measured_peaks()["sustained"],
+                "gflop_per_frame": cfg6.flops_per_frame() / 1e9, "finite": bool(torch.isfinite(o6.float()).all()),
+                "kernels_ms_per_step": {k: v[0] / 3 for k, v in sorted(prof6.items(), key=lambda kv: -kv[1][0])},
+                "note": "InternViT-6B 48L (D=3200, 25x128, I=12800, RMSNorm + q/k RMSNorm) + mlp1 -> 6144, random-init weights "
+                        "generated on the device, one replica per GPU (weak scaling)"}
+            eng6.close()
+            del eng6, pv6
+        except Exception as e:  # a side measurement must never take the bench line down
+            extra["config5_internvit_6b"] = {"unavailable": repr(e)[:300]}
+
+    ms = max_over_ranks(ms_local)
+    ms_e2e = max_over_ranks(ms_e2e_local)
+    rank_ms = [ms_local / args.steps]
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        t = torch.tensor([ms_local / args.steps], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x[0]) for x in allt]
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt[0])
@@ -324,19 +488,27 @@ def run_native(args, rank, local_rank, world, out):
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("gemm_dram_bytes_per_launch")
+        att = kernels.get("attention", {})
+        # attention's own floor: one ex2 per score on the 16-lane/clk/SM MUFU at the clock seen under load
+        exps = cfg.num_layers * frames * cfg.num_heads * cfg.tokens * cfg.tokens
+        mufu_floor_ms = exps / (148 * 16 * (clocks["sm_mhz"] or 1965) * 1e6) * 1e3 if att else None
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": frames, "clips_per_step_per_gpu": n_clips,
-                       "micro_batch_tiles": eng.max_tiles, "parallelism": f"dp{world} (clips sharded, replicas of 0.6 GB weights)",
+                       "micro_batch_tiles": eng.max_tiles, "parallelism": f"dp{world} (clips sharded, replicas of 0.6 GB weights; "
+                       "one all-gather of the visual tokens at the end of the timed region)",
                        "l2": f"{R} rotating input batches; ~{eng.lib.aigv_workspace_bytes(eng._h, eng.max_tiles) / 2**30:.1f} GiB "
                              "activation working set per step >> 126 MB L2",
                        "gflop_per_frame": cfg.flops_per_frame() / 1e9},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": host[0].numel() * 2,
-                    "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps,
+                    "path": f"pinned uint8 {fh}x{fw} RGB frames -> H2D -> aigv_preprocess_u8 (Pillow-exact resize, normalise, bf16) -> "
+                            "aigv_extract_feature -> D2H of the visual tokens; copies double buffered on side streams"},
             "gpu_launches": launches,
+            "rank_ms_per_step": rank_ms,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05 cta_group::2, all GEMM launches of the timed steps)",
                          "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["sustained"]) if achieved else None, "traffic": traffic,
@@ -344,9 +516,20 @@ def run_native(args, rank, local_rank, world, out):
                          "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
                          "flop_per_launch_avg": gemm_fl / max(gemm_launches, 1),
                          "whole_step_frac": value / world * cfg.flops_per_frame() / 1e12 / peaks["sustained"]},
+            "roofline_attention": ({"bound": "tensor + MUFU(ex2)", "kernel": "attention_fwd2_kernel<64> (tcgen05, persistent)",
+                                    "achieved": att.get("tflops"), "peak": peaks["sustained"], "unit": "TFLOP/s",
+                                    "frac": att["tflops"] / peaks["sustained"], "ms_per_step": att["ms_per_step"],
+                                    "mufu_floor_ms_per_step": mufu_floor_ms,
+                                    "frac_of_mufu_floor": mufu_floor_ms / att["ms_per_step"]} if att else None),
             "kernels": kernels,
             "bandwidth_kernels": {k: dict(v, frac_of_hbm_peak=v["GBps"] / peaks["hbm"]) for k, v in bw.items()},
+            "extra": extra,
         }
+        if world == 1 and not args.no_ref_gpu:
+            try:
+                line["reference_gpu_stack"] = reference_gpu_stack(cfg, sd, frames, dev)
+            except Exception as e:  # the comparator must never take the bench line down
+                line["reference_gpu_stack"] = {"unavailable": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             fps, secs = cpu_oracle_fps(cfg, sd, args.cpu_baseline_frames)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
@@ -390,6 +573,9 @@ def main():
     ap.add_argument("--cpu-baseline-frames", type=int, default=16, help="native arm: frames timed on the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-GPU-stack comparator (cuBLASLt / FA2)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 3 / 4 / 5 side measurements")
+    ap.add_argument("--no-6b", action="store_true", help="skip the InternViT-6B (config 5) side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

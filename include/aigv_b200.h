@@ -14,7 +14,8 @@
  * Conventions: plain C types only; every function returns 0 on success or a negative aigv_status and never throws;
  * all device work is enqueued asynchronously on the given stream (a cudaStream_t passed as void*), with no hidden
  * synchronisation or allocation after aigv_finalize_weights (the workspace is owned by the handle and sized by
- * cfg.max_tiles; larger calls are micro-batched); one handle per (process, device); a handle is not thread-safe.
+ * cfg.max_tiles; larger calls are micro-batched); a handle belongs to the device that was current at aigv_create (make it
+ * current for every call; several handles on several devices of one process are fine); a handle is not thread-safe.
  * Pointers are device pointers unless stated otherwise.
  */
 #ifndef AIGV_B200_H_
@@ -93,7 +94,9 @@ int64_t aigv_launch_count(const aigv_handle* h);
  * aigv_preprocess_u8 = dynamic_preprocess resize+crop(+thumbnail) (dataset.py:715-738) fused with build_transform
  * (dataset.py:268-274) and the bf16 cast. frames: uint8 HWC RGB [n, H, W, 3] with the given byte strides. Writes
  * n * (gi*gj + (thumb && gi*gj>1)) tiles, frame-major, tiles row-major then thumbnail. tiles_u8 (optional, may be NULL)
- * receives the uint8 HWC tiles before normalisation. */
+ * receives the uint8 HWC tiles before normalisation. The first call for a new (H, W, grid) builds and uploads the tap
+ * tables synchronously; every later call is asynchronous on `stream`. Sources whose down-scale window does not fit in
+ * shared memory (beyond about 8x, i.e. larger than 4K) return AIGV_ERR_UNSUPPORTED. */
 int aigv_tile_grid(int width, int height, int min_num, int max_num, int image_size, int* gi, int* gj);
 int aigv_preprocess_u8(aigv_handle* h, const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
                        int64_t row_stride, int gi, int gj, int thumb, uint8_t* tiles_u8, void* out_bf16, void* stream);

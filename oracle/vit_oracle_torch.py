@@ -36,7 +36,28 @@ def embeddings(pv, sd, cfg, pre="vision_model."):  # VIT:95-107
     return torch.cat([cls, x], dim=1) + sd[pre + "embeddings.position_embedding"]
 
 
+def _flash_attention(x, sd, lp, cfg):
+    """The reference's GPU attention path: InternAttention._flash_attn (VIT:162-177) -> FlashAttention.forward
+    (flash_attention.py:44-56): qkv packed as [(B*S), 3, H, D], cu_seqlens = arange(0, (B+1)*S, S), non-causal,
+    softmax_scale None (= D^-0.5), dropout 0. Needs the flash-attn wheel, CUDA and fp16/bf16 (flash_attention.py:41-42).
+    Used by bench.py's reference_gpu_stack comparator only."""
+    from flash_attn import flash_attn_varlen_qkvpacked_func
+    n, s, d = x.shape
+    h, hd = cfg.num_heads, cfg.head_dim
+    qkv = F.linear(x, sd[lp + "attn.qkv.weight"], sd.get(lp + "attn.qkv.bias")).view(n, s, 3, h, hd)
+    if cfg.qk_normalization:  # VIT:166-170
+        q, k, v = qkv.unbind(2)
+        q = _rms(q.flatten(-2, -1), sd[lp + "attn.q_norm.weight"], cfg.layer_norm_eps).view(n, s, h, hd)
+        k = _rms(k.flatten(-2, -1), sd[lp + "attn.k_norm.weight"], cfg.layer_norm_eps).view(n, s, h, hd)
+        qkv = torch.stack([q, k, v], dim=2)
+    cu = torch.arange(0, (n + 1) * s, step=s, dtype=torch.int32, device=x.device)
+    ctx = flash_attn_varlen_qkvpacked_func(qkv.reshape(n * s, 3, h, hd), cu, s, 0.0, softmax_scale=None, causal=False)
+    return F.linear(ctx.reshape(n, s, d), sd[lp + "attn.proj.weight"], sd[lp + "attn.proj.bias"])
+
+
 def attention(x, sd, lp, cfg):  # VIT:143-160 (_naive_attn)
+    if getattr(cfg, "_use_flash_attn", False) or sd.get("__use_flash_attn__") is not None:
+        return _flash_attention(x, sd, lp, cfg)
     n, s, d = x.shape
     h, hd = cfg.num_heads, cfg.head_dim
     qkv = F.linear(x, sd[lp + "attn.qkv.weight"], sd.get(lp + "attn.qkv.bias"))

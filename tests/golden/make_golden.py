@@ -92,8 +92,8 @@ def build_reference(cfg, sd_np, dtype=torch.float32):
     return s
 
 
-def golden_tower(name, cfg, n_frames, w_seed, x_seed, full_store):
-    sd = synth.make_weights(cfg, seed=w_seed)
+def golden_tower(name, cfg, n_frames, w_seed, x_seed, full_store, weights=synth.make_weights):
+    sd = weights(cfg, seed=w_seed)
     pv = synth.make_pixel_values(n_frames, cfg, seed=x_seed)
     ref = build_reference(cfg, sd)
     with torch.no_grad():
@@ -156,12 +156,32 @@ def main():
     install_stubs()
     torch.manual_seed(0)
     metas = {}
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:  # regenerate selected towers only, keeping the other entries of golden_meta.json
+        with open(os.path.join(HERE, "golden_meta.json")) as f:
+            metas = json.load(f)
+        if "tiny_stress" in only:
+            metas["tiny_stress"] = golden_tower("tiny_stress", cfgmod.tiny(), n_frames=2, w_seed=106, x_seed=107,
+                                                full_store=False, weights=synth.make_stress_weights)
+        if "vit6b_l1" in only:
+            metas["vit6b_l1"] = golden_tower("vit6b_l1", cfgmod.internvit_6b(num_layers=1), n_frames=1, w_seed=104,
+                                             x_seed=105, full_store=False)
+        with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
+            json.dump(metas, f, indent=1)
+        return
     metas["tiny"] = golden_tower("tiny", cfgmod.tiny(), n_frames=2, w_seed=100, x_seed=101, full_store=True)
     tiny_rms = cfgmod.tiny(hidden_size=256, num_heads=2, intermediate_size=512, qkv_bias=False, qk_normalization=True,
                            norm_type="rms_norm", initializer_factor=0.1)
     metas["tiny_rms"] = golden_tower("tiny_rms", tiny_rms, n_frames=1, w_seed=102, x_seed=103, full_store=False)
     metas["vit300m"] = golden_tower("vit300m", cfgmod.internvit_300m(llm_hidden=2048), n_frames=1, w_seed=0, x_seed=1,
                                     full_store=False)
+    # InternViT-6B block geometry at its REAL width (config 5): D=3200, 25 heads x 128, I=12800, RMSNorm, q/k RMSNorm over
+    # all heads, no qkv bias, layer scale 0.1, projector 12800 -> 6144; one layer keeps the CPU run to seconds
+    metas["vit6b_l1"] = golden_tower("vit6b_l1", cfgmod.internvit_6b(num_layers=1), n_frames=1, w_seed=104, x_seed=105,
+                                     full_store=False)
+    # "trained-like" statistics at the tiny width: peaked attention, +-300 outlier channels, layer scales 0.1 .. 1
+    metas["tiny_stress"] = golden_tower("tiny_stress", cfgmod.tiny(), n_frames=2, w_seed=106, x_seed=107,
+                                        full_store=False, weights=synth.make_stress_weights)
     metas["preprocess"] = golden_preprocess()
     with open(os.path.join(HERE, "golden_meta.json"), "w") as f:
         json.dump(metas, f, indent=1)

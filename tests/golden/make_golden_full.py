@@ -128,8 +128,15 @@ def golden_case(name, vis, n_frames, seeds):
     sens = float(np.abs(outp["score1"].numpy() - score).max())
     # the oracle restatement fed with the reference's own embeddings (pins oracle/head_oracle.py)
     o = ho.stage2_forward(cap["vit"].numpy(), pv, ids, ho.to_torch(sd_head), llm, synth.IMG_CONTEXT_ID)
+    # for calibration: the score the reference's OWN bf16 vision path (its production dtype, stage2_eval.py:932) gives
+    ref16 = mg.build_reference(vis, sd_vis, dtype=torch.bfloat16)
+    with torch.no_grad():
+        e16 = ref16.extract_feature(torch.from_numpy(pv).to(torch.bfloat16)).float().numpy()
+    o16 = ho.stage2_forward(e16, pv, ids, ho.to_torch(sd_head), llm, synth.IMG_CONTEXT_ID)
+    d16 = abs(float(o16["score1"][0]) - float(score[0]))
     hid = cap["hid"][:, -4, :].numpy()
-    print(name, "score1", score, "pre", cap["pre"].reshape(-1).numpy(), "| oracle", o["score1"], "| dscore @1e-2 noise", sens)
+    print(name, "score1", score, "pre", cap["pre"].reshape(-1).numpy(), "| oracle", o["score1"], "| dscore @1e-2 noise", sens,
+          "| reference bf16 vision path dscore", d16)
     logits_arg = out["logit"].numpy()
     np.savez_compressed(os.path.join(HERE, f"full_{name}.npz"), score1=score.astype(np.float32),
                         score_pre=cap["pre"].reshape(-1).numpy().astype(np.float32), hidden_m4=hid.astype(np.float32),
@@ -138,6 +145,7 @@ def golden_case(name, vis, n_frames, seeds):
     assert abs(float(o["score1"][0]) - float(score[0])) < 1e-3 and np.array_equal(o["logit"], logits_arg)
     return dict(name=name, vis_cfg=vis.to_dict(), llm=llm, n_frames=n_frames, seeds=seeds, fc5_scale=fc5_scale,
                 n_tokens=int(ids.shape[1]), score1=float(score[0]), score_sensitivity_1e2=sens,
+                ref_bf16_vision_dscore=d16,
                 oracle_score1=float(o["score1"][0]), vit_absmax=float(cap["vit"].abs().max()), torch=torch.__version__)
 
 

@@ -51,7 +51,8 @@ def test_score1_and_logits_through_the_seam(golden_dir, name):
     decided = (top2[:, 1] - top2[:, 0]) > 1e-2 * np.abs(ref_logits).max()
     same = o["logit"][-48:] == g["logit_tail"]
     print(f"{name}: reference score1 {float(g['score1'][0]):.4f}  CUDA-embeddings score1 {float(o['score1'][0]):.4f} "
-          f"|d| {d_score:.2e} (tol {SCORE_TOL}; a 1e-2 token perturbation moves it {meta['score_sensitivity_1e2']:.3f}); "
+          f"|d| {d_score:.2e} (tol {SCORE_TOL}; the reference's own bf16 vision path: {meta['ref_bf16_vision_dscore']:.2e}; a 1e-2 token "
+          f"perturbation moves it {meta['score_sensitivity_1e2']:.3f}); "
           f"embeddings e_max {e_emb:.2e}; hidden[-4] e_max/e_l2 {e_hid}; logits argmax equal {int(same.sum())}/48 "
           f"({int(decided.sum())} decided)")
     assert e_emb < 2e-2

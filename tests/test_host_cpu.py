@@ -151,3 +151,40 @@ def test_plugin_falls_back_while_training_and_refuses_other_configs():
     assert plugin.install(m) is None and m.extract_feature(None) == "original"   # select_layer != -1: untouched
     with pytest.raises(ValueError):
         plugin.refresh(m)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_tile_grid_matches_the_reference_function_incl_ties():
+    """aigv_tile_grid (the one implementation the product uses) against the reference's find_closest_aspect_ratio
+    (dataset.py:685-699) with its candidate set (dataset.py:707-710), over a grid of sizes incl. exact |ratio| ties such as
+    1280x1024 (aspect 1.25 is equidistant from 1:2... no: from 1/1 and 3/2), 800x640, 1000x500."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden as mg
+    mg.install_stubs()
+    from internvl.train.dataset import find_closest_aspect_ratio
+    n = 0
+    for mx in (1, 2, 6, 12):
+        tr = sorted(set((i, j) for k in range(1, mx + 1) for i in range(1, k + 1) for j in range(1, k + 1)
+                        if 1 <= i * j <= mx), key=lambda x: x[0] * x[1])
+        for w in list(range(100, 2000, 97)) + [1280, 1024, 800, 640, 1000, 500, 1500, 750]:
+            for h in list(range(100, 2000, 89)) + [1024, 1280, 640, 800, 500, 1000, 600, 400]:
+                assert tuple(tiling.tile_grid(w, h, 1, mx, 448)) == tuple(find_closest_aspect_ratio(w / h, tr, w, h, 448)), (w, h, mx)
+                n += 1
+    assert n > 2000
+
+
+def test_safetensors_roundtrip_and_selective_read(tmp_path):
+    from aigv_assessor_b200 import checkpoint
+    cfg = config.tiny()
+    sd = synth.make_weights(cfg, seed=3)
+    extra = {"language_model.model.tok_embeddings.weight": np.ones((7, 5), np.float32)}
+    p = str(tmp_path / "model.safetensors")
+    bf = [k for k in sd if k.endswith(".weight") and sd[k].ndim == 2]
+    checkpoint.write_safetensors(p, {**sd, **extra}, bf16_names=bf)
+    got = checkpoint.load_checkpoint_dir(str(tmp_path))
+    assert set(got) == set(sd)                      # the LLM tensor is skipped
+    assert all(np.array_equal(got[k], sd[k]) for k in sd)   # bf16 storage is exact for bf16-representable values
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        checkpoint.load_checkpoint_dir(str(empty))
