@@ -39,6 +39,8 @@
 // tensor pipe consumes, half of every block's keys per warp -- so no tile is spent on one row.
 // A masked tail block multiplies P == 0 with V rows of the NEXT frame (TMA zero-fills past the end of the matrix);
 // with finite activations that contributes exactly nothing.
+#include <type_traits>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -594,7 +596,10 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             float l_run = 0.f;
             float s_t = 0.f;          // the lone tail key's score (log2 units)
 
-            for (int j = 0; j < n_blocks; ++j) {
+            // One (tile, block) step. kMasked selects the copy that masks a ragged tail block: kept out of the hot loop (its
+            // 128 selects sat between the tcgen05.ld and the row max of EVERY block, jumped over).
+            auto softmax_block = [&](const int j, auto masked_tag) {
+                constexpr bool kMasked = decltype(masked_tag)::value;
                 const uint32_t b = sb;
                 const uint32_t tm_s = tm_lane + b * BKV;
                 mbar_wait(&s_full[b], sph);
@@ -604,7 +609,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
                     for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(tm_s + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
                     tmem_ld_wait();
-                    if (j >= n_full) {  // masked tail block (never taken for ViT sequences)
+                    if (kMasked) {  // masked tail block (never taken for ViT sequences)
 #pragma unroll
                         for (int c = 0; c < BKV; ++c)
                             if (c >= tail_valid) v[c] = 0xff800000u;
@@ -619,7 +624,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     }
                     const float mxs = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
                     const bool need = mxs > m_ref + RESCALE_THRESHOLD;  // always true for block 0 (m_ref = -inf)
-                    if (__any_sync(0xffffffffu, need)) {                 // warp-uniform: TMEM ops are warp-collective
+                    if (__builtin_expect(__any_sync(0xffffffffu, need), 0)) {  // warp-uniform: TMEM ops are warp-collective
                         const float new_ref = need ? mxs : m_ref;
                         if (j > 0) {
                             // O must be quiescent: wait for this tile's previous P V (ring slot (n_pv-1) % PVR, use
@@ -709,6 +714,11 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&q_empty[qb]);
                 }
+            };
+            {
+                int j = 0;
+                for (; j < n_full; ++j) softmax_block(j, std::false_type{});
+                if (j < n_blocks) softmax_block(j, std::true_type{});
             }
 
             // epilogue: fold the lone tail key in (exact reference update), normalise, store
