@@ -13,9 +13,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaigv_b200.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention2_tcgen05.cu", "rowops.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention2_tcgen05.cu", "rowops.cu", "preprocess.cu",
+           "llm_glue.cu"]
 HEADERS = ["kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "aigv_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-t", "0",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -30,12 +31,33 @@ def _nvcc() -> str:
     raise AigvError("nvcc not found; cannot build libaigv_b200.so")
 
 
+def source_hash() -> str:
+    """sha256 over every source / header the library is built from (compiled in as AIGV_SRC_HASH, returned by
+    aigv_source_hash()): load() compares it with the sources on disk, so an edited .cu can never silently run an old
+    binary, wherever file times got lost (the snapshot that travels to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    for s in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, s), "rb") as f:
+            h.update(s.encode())
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def _built_hash(path: str) -> str | None:
+    try:
+        lib = C.CDLL(path)
+        fn = lib.aigv_source_hash
+        fn.restype = C.c_char_p
+        return fn().decode()
+    except (OSError, AttributeError):
+        return None
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return _built_hash(LIB_PATH) != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -43,7 +65,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     extra = os.environ.get("AIGV_NVCC_EXTRA", "").split()  # experiments only, e.g. -DAIGV_ATTN_MIN_CTAS=3
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, f'-DAIGV_SRC_HASH="{source_hash()}"', "-o", LIB_PATH,
+           *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,6 +90,7 @@ _P = C.c_void_p
 _F = C.POINTER(C.c_float)
 SIGNATURES = {
     "aigv_version": (C.c_char_p, []),
+    "aigv_source_hash": (C.c_char_p, []),
     "aigv_status_string": (C.c_char_p, [C.c_int]),
     "aigv_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(_P)]),
     "aigv_destroy": (None, [_P]),
@@ -93,6 +117,8 @@ SIGNATURES = {
     "aigv_assemble_tokens_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "aigv_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_exp2_poly": (C.c_int, [_P, _P, C.c_int, _P]),
+    "aigv_splice_tokens": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
+    "aigv_mlpscore": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_int, _P]),
     "aigv_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "aigv_rmsnorm_inplace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_im2col": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
@@ -108,11 +134,13 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise AigvError(f"{LIB_PATH} is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
-        build()
-    path = os.environ.get("AIGV_LIB", LIB_PATH)  # development: A/B a prebuilt variant of the same ABI
+    path = os.environ.get("AIGV_LIB")  # development: A/B a prebuilt variant of the same ABI (no staleness check)
+    if not path:
+        path = LIB_PATH
+        if _stale():  # missing, or built from other sources than the ones on disk
+            if not build_if_missing:
+                raise AigvError(f"{LIB_PATH} is missing or stale; run `python -c 'import __graft_entry__ as g; g.build()'`")
+            build(force=True)
     try:
         lib = C.CDLL(path)
     except OSError as e:  # pragma: no cover

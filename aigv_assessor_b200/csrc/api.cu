@@ -276,7 +276,12 @@ int build_act_maps(aigv_handle* h, int n) {
 
 extern "C" {
 
-const char* aigv_version(void) { return "aigv_b200 0.1 (sm_100a tcgen05/TMA)"; }
+const char* aigv_version(void) { return "aigv_b200 0.2 (sm_100a tcgen05/TMA)"; }
+
+#ifndef AIGV_SRC_HASH
+#define AIGV_SRC_HASH "unknown"
+#endif
+const char* aigv_source_hash(void) { return AIGV_SRC_HASH; }
 
 const char* aigv_status_string(int s) {
     switch (s) {
@@ -952,6 +957,30 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
 int aigv_exp2_poly(const float* x, float* y, int n, void* stream) {
     if (!x || !y || n <= 0) return AIGV_ERR_INVALID;
     AIGV_TRY0(launch_exp2_poly_test(x, y, n, static_cast<cudaStream_t>(stream)));
+    return AIGV_OK;
+}
+
+int aigv_splice_tokens(const int64_t* input_ids, const void* tok_embeddings_bf16, const void* vit_embeds_bf16,
+                       const void* motion_embeds_bf16, void* out_bf16, int32_t* work, int B, int N, int C, int V, int n_vit,
+                       int64_t img_context_token_id, void* stream) {
+    if (!input_ids || !tok_embeddings_bf16 || !vit_embeds_bf16 || !motion_embeds_bf16 || !out_bf16 || !work)
+        return AIGV_ERR_INVALID;
+    cudaError_t e = launch_splice_tokens(reinterpret_cast<const long long*>(input_ids),
+                                         static_cast<const __nv_bfloat16*>(tok_embeddings_bf16),
+                                         static_cast<const __nv_bfloat16*>(vit_embeds_bf16),
+                                         static_cast<const __nv_bfloat16*>(motion_embeds_bf16),
+                                         static_cast<__nv_bfloat16*>(out_bf16), work, B, N, C, V, n_vit,
+                                         static_cast<long long>(img_context_token_id), static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidValue) return AIGV_ERR_INVALID;
+    return e == cudaSuccess ? AIGV_OK : AIGV_ERR_CUDA;
+}
+
+int aigv_mlpscore(const float* x, int ldx, const float* const* weights, const float* const* biases, float* score,
+                  float* pre_relu, int n, void* stream) {
+    if (!x || !weights || !biases || !score || ldx < 4096) return AIGV_ERR_INVALID;
+    for (int l = 0; l < 5; ++l)
+        if (!weights[l] || !biases[l]) return AIGV_ERR_INVALID;
+    AIGV_TRY0(launch_mlpscore(x, ldx, weights, biases, score, pre_relu, n, static_cast<cudaStream_t>(stream)));
     return AIGV_OK;
 }
 

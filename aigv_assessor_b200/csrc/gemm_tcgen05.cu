@@ -154,6 +154,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     tc_fence_before();
     cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / TMA credit / multicast commit
+    __syncthreads();      // (the cluster barrier already orders the TMEM-slot write; compute-sanitizer racecheck only
+                          // recognises the CTA barrier and otherwise reports the slot read below as a hazard)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -253,7 +255,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                          4u * static_cast<uint32_t>(N - c0 < SLICE_COLS ? N - c0 : SLICE_COLS));
                 };
 #ifndef AIGV_GEMM_PREFETCH_NEXT
-#define AIGV_GEMM_PREFETCH_NEXT 1
+#define AIGV_GEMM_PREFETCH_NEXT 0   // measured (profiles/r2c_ncu_gemm_summary.txt): +110 MB (proj) / +216 MB (fc2) of DRAM re-reads per launch and 6 % slower proj -- the lines are evicted again before the TMA fetch wants them
 #endif
                 if (AIGV_GEMM_PREFETCH_NEXT) {
                     if (tile == pair) prefetch_rows(tile);

@@ -76,6 +76,16 @@ cudaError_t launch_attention2(const CUtensorMap& tm_q, const CUtensorMap& tm_kv,
 // Test hook: y[i] = the attention kernel's FMA-pipe 2^x (exp2_poly2) for x[i] (softmax arguments are <= 8).
 cudaError_t launch_exp2_poly_test(const float* x, float* y, int n, cudaStream_t stream);
 
+// ---- above the seam (llm_glue.cu) ---------------------------------------------------
+// Visual-token splice (eval2 :324,351-378). work: int32 [B*N + 2*B + 1] scratch; work[B*N + 2*B] is an error flag the caller
+// may read back (1 = token id out of range, 2/4 = number of visual rows does not match the <IMG_CONTEXT> slots).
+cudaError_t launch_splice_tokens(const long long* ids, const __nv_bfloat16* tok, const __nv_bfloat16* vit,
+                                 const __nv_bfloat16* motion, __nv_bfloat16* out, int* work, int B, int N, int C, int V,
+                                 int n_vit, long long ctx_id, cudaStream_t stream);
+// mlpscore head (eval2 :82-94): x fp32 [n, >=4096] with row stride ldx; w[l] fp32 [out_l, in_l], b[l] fp32 [out_l].
+cudaError_t launch_mlpscore(const float* x, int ldx, const float* const* w, const float* const* b, float* score, float* pre,
+                            int n, cudaStream_t stream);
+
 // Opt a kernel in to > 48 KiB of dynamic shared memory once PER DEVICE (function attributes are per device: a second
 // engine on another GPU of the same process needs its own opt-in). `mask` is the call site's static bit set.
 inline cudaError_t ensure_smem_optin(const void* kernel, int bytes, unsigned long long& mask) {

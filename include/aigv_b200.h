@@ -60,6 +60,8 @@ typedef struct aigv_cfg {
 } aigv_cfg;
 
 const char* aigv_version(void);
+/* Hash of the sources this binary was built from (the Python loader refuses / rebuilds a stale library). */
+const char* aigv_source_hash(void);
 const char* aigv_status_string(int status);
 
 /* Lifecycle. Replaces InternVLChatModel.__init__'s vision_model/mlp1 construction (eval2 :218-243) for this path. */
@@ -132,6 +134,19 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
 /* Test hook: y[i] = 2^x[i] exactly as the attention kernel evaluates the share of its exponentials that runs on the
  * FMA pipe instead of MUFU (Cody-Waite split + cubic; x fp32 [n], device pointers). */
 int aigv_exp2_poly(const float* x, float* y, int n, void* stream);
+/* Above the seam (first pieces). aigv_splice_tokens = InternVLChatModel.forward's
+ * input_embeds = tok_embeddings(input_ids) with every <IMG_CONTEXT> slot but the last of a sample overwritten by the next
+ * visual token (flattened sample-major order, like the boolean-mask assignment) and the last one by the sample's motion
+ * token (modeling_internvl_chat.py eval2 :324,351-378). work: int32 scratch of B*N + 2*B + 1 elements; its last element is
+ * an error flag (0 = ok; 1: a token id outside [0,V); 2/4: n_vit does not match the slots -- the case where the reference
+ * falls into its except branch). aigv_mlpscore = the MLP head of eval2 :82-94 (ReLU after every layer incl. the last) on
+ * x[n, 4096] (row stride ldx), weights[l] fp32 [out_l, in_l] for 4096-1024-256-64-16-1; pre_relu (optional) receives the
+ * last layer's value before its ReLU. */
+int aigv_splice_tokens(const int64_t* input_ids, const void* tok_embeddings_bf16, const void* vit_embeds_bf16,
+                       const void* motion_embeds_bf16, void* out_bf16, int32_t* work, int B, int N, int C, int V, int n_vit,
+                       int64_t img_context_token_id, void* stream);
+int aigv_mlpscore(const float* x, int ldx, const float* const* weights, const float* const* biases, float* score,
+                  float* pre_relu, int n, void* stream);
 int aigv_layernorm(const float* x, const float* w, const float* b, void* y_bf16, int rows, int D, float eps, int rms,
                    void* stream);
 int aigv_rmsnorm_inplace(void* x_bf16, const float* w, int rows, int D, int ld, int col0, float eps, void* stream);
