@@ -13,7 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaigv_b200.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "attention2_tcgen05.cu", "rowops.cu", "preprocess.cu",
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention2_tcgen05.cu", "rowops.cu", "preprocess.cu",
            "llm_glue.cu"]
 HEADERS = ["kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "aigv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-t", "0",

@@ -74,22 +74,10 @@ static int device_num_sms() {
     return sms[dev];
 }
 
-// Attention dispatcher: the round-2 persistent kernel by default; AIGV_ATTN_V1=1 selects the round-1 kernel (A/B runs;
-// it needs tokens % 64 <= 32).
-static bool attention_use_v1() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("AIGV_ATTN_V1");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
-}
-// tm_q: [128, 64] boxes; tm_kv / tm_tail: the round-1 kernel's 64- and 32-row boxes; tm_kv2: the round-2 K/V box.
-static cudaError_t run_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
-                                 const CUtensorMap& tm_kv2, const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S,
-                                 int heads, int head_dim, float scale, int num_sms, cudaStream_t st) {
-    if (attention_use_v1()) return launch_attention(tm_q, tm_kv, tm_tail, qkv, out, frames, S, heads, head_dim, scale, st);
-    return launch_attention2(tm_q, tm_kv2, qkv, out, frames, S, heads, head_dim, scale, num_sms, st);
+static cudaError_t run_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const __nv_bfloat16* qkv,
+                                 __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float scale, int num_sms,
+                                 cudaStream_t st) {
+    return launch_attention2(tm_q, tm_kv, qkv, out, frames, S, heads, head_dim, scale, num_sms, st);
 }
 
 // ------------------------------------------------------------------------------------------------ dtype conversion
@@ -140,7 +128,7 @@ struct LayerW {
 
 struct ActMaps {
     int n = -1;
-    CUtensorMap patches, xn, attn, h, ps, m1, qkv_q, qkv_kv, qkv_tail, qkv_kv2;   // TMA loads (GEMM A operands, attention)
+    CUtensorMap patches, xn, attn, h, ps, m1, qkv_q, qkv_kv;   // TMA loads (GEMM A operands, attention)
     CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out, xb_out;      // TMA stores / reduce-adds (GEMM outputs)
 };
 
@@ -256,10 +244,8 @@ int build_act_maps(aigv_handle* h, int n) {
     r |= make_tmap_bf16_2d(&h->maps.h, h->hbuf, M, h->I, h->I, ba, bc);
     r |= make_tmap_bf16_2d(&h->maps.ps, h->ps, Mo, h->W4, h->W4, ba, bc);
     r |= make_tmap_bf16_2d(&h->maps.m1, h->m1, Mo, h->C, h->C, ba, bc);
-    r |= make_tmap_bf16_2d(&h->maps.qkv_q, h->qkv, M, 3 * h->D, 3 * h->D, attention_q_rows(), 64);
-    r |= make_tmap_bf16_2d(&h->maps.qkv_kv, h->qkv, M, 3 * h->D, 3 * h->D, attention_kv_rows(), 64);
-    r |= make_tmap_bf16_2d(&h->maps.qkv_tail, h->qkv, M, 3 * h->D, 3 * h->D, attention_tail_rows(h->S), 64);
-    r |= make_tmap_bf16_2d(&h->maps.qkv_kv2, h->qkv, M, 3 * h->D, 3 * h->D, attention2_kv_box_rows(h->hd), 64);
+    r |= make_tmap_bf16_2d(&h->maps.qkv_q, h->qkv, M, 3 * h->D, 3 * h->D, attention2_q_box_rows(), 64);
+    r |= make_tmap_bf16_2d(&h->maps.qkv_kv, h->qkv, M, 3 * h->D, 3 * h->D, attention2_kv_box_rows(h->hd), 64);
     const int cr = gemm_box_rows_c(), cb = gemm_box_cols_c(false), cf = gemm_box_cols_c(true);
     r |= make_tmap_2d(&h->maps.pe_out, h->pe, 1, Mp, h->D, h->D, cr, cf);
     r |= make_tmap_2d(&h->maps.x_out, h->x, 1, M, h->D, h->D, cr, cf);
@@ -342,8 +328,6 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
     h->T = (h->g / 2) * (h->g / 2);
     if (h->hd != 64 && h->hd != 128)
         return bad(AIGV_ERR_UNSUPPORTED, "attention kernel covers head_dim 64 (InternViT-300M) and 128 (InternViT-6B)");
-    if (attention_use_v1() && h->S % 64 > 32)
-        return bad(AIGV_ERR_UNSUPPORTED, "the round-1 attention kernel needs (tokens mod 64) <= 32");
     if (h->g % 2) return bad(AIGV_ERR_UNSUPPORTED, "patch grid must be even for the 2x2 pixel shuffle");
     if (h->D % 32 || h->I % 32 || h->C % 32 || cfg->patch_size % 2)
         return bad(AIGV_ERR_UNSUPPORTED, "hidden/intermediate/llm widths must be multiples of 32");
@@ -649,7 +633,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
         if (h->cfg.qk_normalization) {
             AIGV_LAUNCH(K_QKNORM, launch_rmsnorm_bf16_inplace(h->qkv, w.qnw, M, D, 3 * D, 0, eps, st, w.knw, D), "q_norm+k_norm");
         }
-        AIGV_LAUNCH(K_ATTENTION, run_attention(h->maps.qkv_q, h->maps.qkv_kv, h->maps.qkv_tail, h->maps.qkv_kv2, h->qkv, h->attn, n, S, h->H, h->hd, scale,
+        AIGV_LAUNCH(K_ATTENTION, run_attention(h->maps.qkv_q, h->maps.qkv_kv, h->qkv, h->attn, n, S, h->H, h->hd, scale,
                                                h->num_sms, st),
                  "attention");
         {
@@ -942,14 +926,11 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
                    void* stream) {
     if (!qkv_bf16 || !out_bf16 || frames <= 0 || S <= 0 || heads <= 0) return AIGV_ERR_INVALID;
     if (head_dim != 64 && head_dim != 128) return AIGV_ERR_UNSUPPORTED;
-    if (attention_use_v1() && S % 64 > 32) return AIGV_ERR_UNSUPPORTED;
     const uint64_t M = (uint64_t)frames * S, D3 = 3ull * heads * head_dim;
-    CUtensorMap tq, tk, tt, tk2;
-    if (make_tmap_bf16_2d(&tq, qkv_bf16, M, D3, D3, attention_q_rows(), 64)) return AIGV_ERR_INVALID;
-    if (make_tmap_bf16_2d(&tk, qkv_bf16, M, D3, D3, attention_kv_rows(), 64)) return AIGV_ERR_INVALID;
-    if (make_tmap_bf16_2d(&tt, qkv_bf16, M, D3, D3, attention_tail_rows(S), 64)) return AIGV_ERR_INVALID;
-    if (make_tmap_bf16_2d(&tk2, qkv_bf16, M, D3, D3, attention2_kv_box_rows(head_dim), 64)) return AIGV_ERR_INVALID;
-    AIGV_TRY0(run_attention(tq, tk, tt, tk2, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
+    CUtensorMap tq, tk;
+    if (make_tmap_bf16_2d(&tq, qkv_bf16, M, D3, D3, attention2_q_box_rows(), 64)) return AIGV_ERR_INVALID;
+    if (make_tmap_bf16_2d(&tk, qkv_bf16, M, D3, D3, attention2_kv_box_rows(head_dim), 64)) return AIGV_ERR_INVALID;
+    AIGV_TRY0(run_attention(tq, tk, static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<__nv_bfloat16*>(out_bf16), frames, S, heads, head_dim, scale,
                             device_num_sms(), static_cast<cudaStream_t>(stream)));
     return AIGV_OK;
 }

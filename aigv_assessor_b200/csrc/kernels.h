@@ -54,17 +54,8 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 
 // ---- attention -------------------------------------------------------------------------------------------------
 // qkv: bf16 [frames*S, 3*D] with channel order (three, head, d); out: bf16 [frames*S, D] (head-major channels).
-// Three maps over the same qkv matrix, boxes [attention_q_rows(), 64], [attention_kv_rows(), 64] and
-// [attention_tail_rows(S), 64].
-int attention_q_rows();
-int attention_kv_rows();
-int attention_tail_rows(int S);
-// qkv: base of the [frames*S, 3*heads*head_dim] matrix the three maps describe (the side query row is read directly).
-cudaError_t launch_attention(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const CUtensorMap& tm_tail,
-                             const __nv_bfloat16* qkv, __nv_bfloat16* out, int frames, int S, int heads, int head_dim,
-                             float softmax_scale, cudaStream_t stream);
-
-// Round-2 persistent kernel (attention2_tcgen05.cu): two maps over the qkv matrix, boxes [attention2_q_box_rows(), 64] (Q
+// Persistent kernel (attention2_tcgen05.cu; the round-1 kernel it replaced is in the history, its measurements in
+// profiles/r2_attention_notes.txt): two maps over the qkv matrix, boxes [attention2_q_box_rows(), 64] (Q
 // tiles) and [attention2_kv_box_rows(head_dim), 64] (K / V blocks); any sequence length; head_dim 64 or 128; num_sms =
 // persistent CTAs to launch.
 int attention2_q_box_rows();
