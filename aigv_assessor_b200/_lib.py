@@ -45,13 +45,18 @@ def source_hash() -> str:
 
 
 def _built_hash(path: str) -> str | None:
+    # read from the file's bytes, not through dlopen: a library dlopen()ed before a rebuild stays mapped under the
+    # same path, and the rebuilt file would then look stale to this process
     try:
-        lib = C.CDLL(path)
-        fn = lib.aigv_source_hash
-        fn.restype = C.c_char_p
-        return fn().decode()
-    except (OSError, AttributeError):
+        with open(path, "rb") as f:
+            data = f.read()
+    except OSError:
         return None
+    i = data.find(b"aigv-src-hash:")
+    if i < 0:
+        return None
+    j = data.find(b"\0", i)
+    return data[i + 14:j].decode(errors="replace")
 
 
 def _stale() -> bool:

@@ -148,7 +148,8 @@ struct Profiler {
 
 struct PlanDev {
     int32_t *kx = nullptr, *bx = nullptr, *ky = nullptr, *by = nullptr;
-    int ksize_x = 0, ksize_y = 0, max_rows = 0, span_bytes = 0;
+    int ksize_x = 0, ksize_y = 0;
+    ResizeGeom geo{};
 };
 
 }  // namespace
@@ -267,7 +268,9 @@ const char* aigv_version(void) { return "aigv_b200 0.2 (sm_100a tcgen05/TMA)"; }
 #ifndef AIGV_SRC_HASH
 #define AIGV_SRC_HASH "unknown"
 #endif
-const char* aigv_source_hash(void) { return AIGV_SRC_HASH; }
+// "aigv-src-hash:" lets the loader read the hash from the file's bytes without dlopen()ing a possibly stale library
+static const char kSrcHash[] = "aigv-src-hash:" AIGV_SRC_HASH;
+const char* aigv_source_hash(void) { return kSrcHash + 14; }
 
 const char* aigv_status_string(int s) {
     switch (s) {
@@ -791,8 +794,7 @@ static int get_plan(aigv_handle* h, int H, int W, int out_w, int out_h, PlanDev*
     PlanDev p;
     p.ksize_x = plan_axis(W, out_w, kx, bx);
     p.ksize_y = plan_axis(H, out_h, ky, by);
-    p.max_rows = plan_max_rows(by, out_h);
-    p.span_bytes = plan_max_span_bytes(bx, out_w);
+    p.geo = plan_geometry(bx, by, out_w, out_h, p.ksize_x, p.ksize_y);
     bool ok = dev_alloc(h, &p.kx, kx.size()) && dev_alloc(h, &p.bx, bx.size()) && dev_alloc(h, &p.ky, ky.size()) &&
               dev_alloc(h, &p.by, by.size());
     if (!ok) return -1;
@@ -818,20 +820,20 @@ int aigv_preprocess_u8(aigv_handle* h, const uint8_t* frames, int n, int H, int 
     const int per_frame = blocks + (with_thumb ? 1 : 0);
     PlanDev* p = nullptr;
     if (get_plan(h, H, W, tile * gi, tile * gj, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
-    if (!preprocess_fits(p->max_rows, p->span_bytes))
+    if (!preprocess_fits(p->geo, p->ksize_x, p->ksize_y))
         return fail(h, AIGV_ERR_UNSUPPORTED, "frame too large for the resize kernel's shared-memory window (" +
                                                  std::to_string(W) + "x" + std::to_string(H) + " -> " + std::to_string(tile * gi) + "x" +
                                                  std::to_string(tile * gj) + "): down-scale factors up to about 8x (4K sources) are covered");
     ResizePlan rp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile * gi, tile * gj};
-    AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, rp, p->max_rows, p->span_bytes, h->lut, tile, gi,
+    AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, rp, p->geo, h->lut, tile, gi,
                                     per_frame, 0, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
              "preprocess");
     if (with_thumb) {
         if (get_plan(h, H, W, tile, tile, &p)) return fail(h, AIGV_ERR_CUDA, "preprocess plan upload failed");
-        if (!preprocess_fits(p->max_rows, p->span_bytes))
+        if (!preprocess_fits(p->geo, p->ksize_x, p->ksize_y))
             return fail(h, AIGV_ERR_UNSUPPORTED, "frame too large for the thumbnail resize's shared-memory window");
         ResizePlan tp{p->kx, p->bx, p->ky, p->by, p->ksize_x, p->ksize_y, tile, tile};
-        AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, tp, p->max_rows, p->span_bytes, h->lut, tile, 1,
+        AIGV_LAUNCH(K_PREPROCESS, launch_preprocess_impl(frames, n, H, W, frame_stride, row_stride, tp, p->geo, h->lut, tile, 1,
                                         per_frame, blocks, tiles_u8, static_cast<__nv_bfloat16*>(out_bf16), st),
                  "preprocess(thumbnail)");
     }

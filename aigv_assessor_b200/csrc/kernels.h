@@ -115,23 +115,26 @@ cudaError_t launch_pixel_shuffle_ln(const float* x, const float* w, const float*
 // Pillow-exact two-pass bicubic (antialias) resize of uint8 HWC frames into square tiles, fused with
 // ToTensor/Normalize (768-entry LUT) and the bf16 cast, written NCHW. Tables live on the device.
 struct ResizePlan {
-    const int32_t* kx;   // [out_w, ksize_x] fixed-point taps
+    const int32_t* kx;   // [out_w, ksize_x] fixed-point taps (ksize_* = table row stride, zero padded to a multiple of 4)
     const int32_t* bx;   // [out_w, 2] xmin, count
     const int32_t* ky;   // [out_h, ksize_y]
     const int32_t* by;   // [out_h, 2]
     int ksize_x, ksize_y;
     int out_w, out_h;    // resized image size (multiples of the tile size)
 };
+struct ResizeGeom {
+    int rows_src, rows_tmp, span_words;  // shared-memory window of one 32x32 output block (see preprocess.cu)
+};
 }  // namespace aigv
 #include <vector>
 namespace aigv {
 // Host: Pillow precompute_coeffs + normalize_coeffs_8bpc for one axis; returns ksize.
 int plan_axis(int in_size, int out_size, std::vector<int32_t>& kk, std::vector<int32_t>& bounds);
-int plan_max_rows(const std::vector<int32_t>& by, int out_h);
-int plan_max_span_bytes(const std::vector<int32_t>& bx, int out_w);
-bool preprocess_fits(int max_rows, int span_bytes);  // does the source window of a 32x32 output block fit in shared memory?
+ResizeGeom plan_geometry(const std::vector<int32_t>& bx, const std::vector<int32_t>& by, int out_w, int out_h,
+                         int ksize_x, int ksize_y);
+bool preprocess_fits(const ResizeGeom& g, int ksize_x, int ksize_y);  // does a block's window fit in shared memory?
 cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
-                                   int64_t row_stride, const ResizePlan& plan, int max_rows, int span_bytes,
+                                   int64_t row_stride, const ResizePlan& plan, const ResizeGeom& geo,
                                    const float* lut, int tile, int tiles_x, int tiles_per_frame, int tile_offset,
                                    uint8_t* tiles_u8, __nv_bfloat16* out, cudaStream_t stream);
 

@@ -12,6 +12,7 @@
 // normalize_coeffs_8bpc (plan_resize below). HBM-bound: reads H*W*3 bytes, writes 3*448*448*2 bytes per tile.
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -23,111 +24,156 @@ namespace {
 
 constexpr int PRECISION_BITS = 32 - 8 - 2;
 constexpr int TX = 32, TY = 32;  // output pixels per block
+constexpr int TMP_STRIDE = TX + 1;  // words per row of the horizontally resampled stage (odd: conflict-free both ways)
 
-__device__ __forceinline__ int clip8(int v) {
-    v >>= PRECISION_BITS;
-    return v < 0 ? 0 : (v > 255 ? 255 : v);
+__device__ __forceinline__ uint32_t clip8(int v) {
+    return static_cast<uint32_t>(__vimin_s32_relu(v >> PRECISION_BITS, 255));   // max(min(v, 255), 0): one VIMNMX
+}
+// byte i of w, zero extended: one PRMT (selector nibble 4 = byte 0 of the zero operand)
+template <int I>
+__device__ __forceinline__ int byte_of(uint32_t w) {
+    return static_cast<int>(__byte_perm(w, 0u, 0x4440u | I));
 }
 
-// One block = a 32x32 block of output pixels of one frame.
-//   phase A: the source rows/columns this block's taps touch are copied into shared memory with coalesced 4-byte loads
-//   phase B: horizontal taps from shared memory -> uint8 rows in shared memory (Pillow's imTemp)
-//   phase C: vertical taps -> uint8 -> LUT -> bf16 NCHW (and optionally the uint8 HWC tile)
-__global__ void __launch_bounds__(256)
-preprocess_kernel(const uint8_t* __restrict__ frames, int H, int W, int64_t frame_stride, int64_t row_stride,
+// One block = a 32x32 block of output pixels of one frame. All shared-memory traffic is 32-bit or wider:
+//   phase A: the source window (rows x bytes this block's taps touch) is copied into shared memory with coalesced
+//            16-byte (or word) loads; the block's tap tables and the bf16 normalisation table are staged next to it
+//   phase B: horizontal taps. Lane = source ROW (odd row stride: no bank conflicts), so a warp shares one output column,
+//            one tap table (broadcast 16-byte loads) and one alignment; the 3 x 4 taps of a chunk come out of three
+//            funnel-shifted words with one PRMT per byte and one IMAD per tap -> packed RGBX word per (row, column)
+//   phase C: vertical taps on the RGBX words (lane = column), uint8 rounding, table look-up, bf16 NCHW stores
+// Tap tables are zero padded to a multiple of 4 taps: padding taps multiply whatever the window holds there (possibly
+// never-written shared memory -- integers, so harmless) by zero.
+__global__ void __launch_bounds__(256, 5)
+preprocess_kernel(const uint8_t* __restrict__ frames, int W, int64_t frame_stride, int64_t row_stride,
                   ResizePlan plan, const float* __restrict__ lut, int tile, int tiles_x, int tiles_per_frame,
-                  int tile_offset, uint8_t* __restrict__ tiles_u8, __nv_bfloat16* __restrict__ out, int max_rows,
-                  int span_bytes, int aligned4) {
+                  int tile_offset, uint8_t* __restrict__ tiles_u8, __nv_bfloat16* __restrict__ out, ResizeGeom geo,
+                  int aligned) {
     extern __shared__ __align__(16) uint8_t sm[];
-    uint8_t* srct = sm;                               // [max_rows][span_bytes] source window
-    uint8_t* tmp = sm + max_rows * span_bytes;        // [max_rows][TX][3] horizontally resampled rows
+    const int ksx = plan.ksize_x, ksy = plan.ksize_y, sw = geo.span_words;
+    int32_t* const kxs = reinterpret_cast<int32_t*>(sm);                        // [TX][ksx]
+    int32_t* const kys = kxs + TX * ksx;                                        // [TY][ksy]
+    uint32_t* const srct = reinterpret_cast<uint32_t*>(kys + TY * ksy);         // [rows_src][sw] source window
+    uint32_t* const tmp = srct + geo.rows_src * sw;                             // [rows_tmp][TMP_STRIDE] RGBX, pass 1
+    __nv_bfloat16* const lutb = reinterpret_cast<__nv_bfloat16*>(tmp + geo.rows_tmp * TMP_STRIDE);  // [3][256]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
-    const int x_last = min(x0 + TX, plan.out_w) - 1;
-    const int y_last = min(y0 + TY, plan.out_h) - 1;
-    const int ysrc0 = plan.by[2 * y0];
-    const int nrows = plan.by[2 * y_last] + plan.by[2 * y_last + 1] - ysrc0;
-    const int xsrc0 = plan.bx[2 * x0];
-    const int xsrc1 = plan.bx[2 * x_last] + plan.bx[2 * x_last + 1];
-    const uint8_t* src = frames + f * frame_stride;
-    const int byte0 = xsrc0 * 3;
-    const int byte1 = xsrc1 * 3;
+    const int nx = min(TX, plan.out_w - x0), ny = min(TY, plan.out_h - y0);
+    const int2* const bx2 = reinterpret_cast<const int2*>(plan.bx) + x0;   // (first source column, taps) per output column
+    const int2* const by2 = reinterpret_cast<const int2*>(plan.by) + y0;
+    const int ysrc0 = __ldg(by2).x;
+    const int2 bl = __ldg(by2 + ny - 1);
+    const int nrows = bl.x + bl.y - ysrc0;
+    // byte offset (within a source row) of srct column 0: 16-byte aligned when the rows can be read with 16-byte loads
+    const int win0 = (__ldg(bx2).x * 3) & (aligned == 2 ? ~15 : ~3);
+    const uint8_t* src = frames + f * frame_stride + static_cast<int64_t>(ysrc0) * row_stride + win0;
 
     // phase A
-    if (aligned4) {
-        const int w0 = byte0 & ~3;                     // window starts at a 4-byte boundary of the row
-        const int nwords = (byte1 - w0 + 3) >> 2;
-        const int row_words = static_cast<int>(row_stride >> 2);
-        for (int idx = threadIdx.x; idx < nrows * nwords; idx += blockDim.x) {
-            const int rr = idx / nwords, ww = idx - rr * nwords;
-            const int word = (w0 >> 2) + ww;
-            uint32_t v = 0;
-            if (word < row_words)                      // never read past the end of the row
-                v = __ldg(reinterpret_cast<const uint32_t*>(src + static_cast<int64_t>(ysrc0 + rr) * row_stride) + word);
-            *reinterpret_cast<uint32_t*>(srct + rr * span_bytes + ww * 4) = v;
-        }
-    } else {
-        const int w0 = byte0;
-        const int nbytes = byte1 - w0;
-        for (int idx = threadIdx.x; idx < nrows * nbytes; idx += blockDim.x) {
-            const int rr = idx / nbytes, bb = idx - rr * nbytes;
-            srct[rr * span_bytes + bb] = src[static_cast<int64_t>(ysrc0 + rr) * row_stride + w0 + bb];
-        }
-    }
-    const int win0 = aligned4 ? (byte0 & ~3) : byte0;  // byte offset (within the row) of srct column 0
-    __syncthreads();
-
-    // phase B: horizontal taps
-    for (int idx = threadIdx.x; idx < nrows * TX; idx += blockDim.x) {
-        const int rr = idx / TX, xx = idx % TX;
-        const int X = x0 + xx;
-        int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
-        if (X < plan.out_w) {
-            const int xmin = plan.bx[2 * X], cnt = plan.bx[2 * X + 1];
-            const int32_t* k = plan.kx + static_cast<size_t>(X) * plan.ksize_x;
-            const uint8_t* p = srct + rr * span_bytes + (xmin * 3 - win0);
-            for (int t = 0; t < cnt; ++t) {
-                const int kk = __ldg(k + t);
-                a0 += p[3 * t + 0] * kk;
-                a1 += p[3 * t + 1] * kk;
-                a2 += p[3 * t + 2] * kk;
+    for (int i = tid; i < nx * ksx; i += 256) kxs[i] = __ldg(plan.kx + static_cast<size_t>(x0) * ksx + i);
+    for (int i = tid; i < ny * ksy; i += 256) kys[i] = __ldg(plan.ky + static_cast<size_t>(y0) * ksy + i);
+    for (int i = tid; i < 768; i += 256) lutb[i] = __float2bfloat16_rn(__ldg(lut + i));
+    {
+        const int2 bxl = __ldg(bx2 + nx - 1);
+        const int need = (bxl.x + bxl.y) * 3 - win0;                 // bytes of the window the real taps read
+        if (aligned == 2) {
+            const int nq = (need + 15) >> 4;                          // 16-byte pieces per row (4 * nq <= sw - 1)
+            const int safe = static_cast<int>((row_stride - win0) >> 4);   // pieces that stay inside the row
+            for (int rr = warp; rr < nrows; rr += 8) {
+                const uint4* g = reinterpret_cast<const uint4*>(src + static_cast<int64_t>(rr) * row_stride);
+                uint32_t* d = srct + rr * sw;
+                for (int q = lane; q < nq; q += 32) {
+                    const uint4 v = q < safe ? __ldg(g + q) : make_uint4(0u, 0u, 0u, 0u);
+                    d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
+                }
+            }
+        } else if (aligned == 1) {
+            const int nw = (need + 3) >> 2;
+            const int safe = static_cast<int>((row_stride - win0) >> 2);
+            for (int rr = warp; rr < nrows; rr += 8) {
+                const uint32_t* g = reinterpret_cast<const uint32_t*>(src + static_cast<int64_t>(rr) * row_stride);
+                for (int ww = lane; ww < nw; ww += 32) srct[rr * sw + ww] = ww < safe ? __ldg(g + ww) : 0u;
+            }
+        } else {
+            const int nw = (need + 3) >> 2;
+            const int nb = W * 3 - win0;
+            for (int rr = warp; rr < nrows; rr += 8) {
+                const uint8_t* g = src + static_cast<int64_t>(rr) * row_stride;
+                for (int ww = lane; ww < nw; ww += 32) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (ww * 4 + b < nb) v |= static_cast<uint32_t>(g[ww * 4 + b]) << (8 * b);
+                    srct[rr * sw + ww] = v;
+                }
             }
         }
-        uint8_t* d = tmp + (rr * TX + xx) * 3;
-        d[0] = static_cast<uint8_t>(clip8(a0));
-        d[1] = static_cast<uint8_t>(clip8(a1));
-        d[2] = static_cast<uint8_t>(clip8(a2));
     }
     __syncthreads();
 
-    // phase C: vertical taps, normalise, write bf16 NCHW (and optionally the uint8 HWC tile)
-    const int tx = threadIdx.x % TX;
-    const int X = x0 + tx;
-    if (X >= plan.out_w) return;
-    for (int yy = threadIdx.x / TX; yy < TY; yy += blockDim.x / TX) {
-        const int Y = y0 + yy;
-        if (Y >= plan.out_h) break;
-        const int ymin = plan.by[2 * Y] - ysrc0, cnt = plan.by[2 * Y + 1];
-        const int32_t* k = plan.ky + static_cast<size_t>(Y) * plan.ksize_y;
-        int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
-        for (int t = 0; t < cnt; ++t) {
-            const int kk = __ldg(k + t);
-            const uint8_t* p = tmp + ((ymin + t) * TX + tx) * 3;
-            a0 += p[0] * kk;
-            a1 += p[1] * kk;
-            a2 += p[2] * kk;
+    // phase B: horizontal taps; items (column, row) in row-fastest order, 256 apart per step: no division in the loop
+    const int half = 1 << (PRECISION_BITS - 1);
+    {
+        const int step_x = 256 / nrows, step_r = 256 - step_x * nrows;
+        int xx = tid / nrows, rr = tid - xx * nrows;
+        while (xx < nx) {
+            const int2 b = __ldg(bx2 + xx);
+            const int boff = b.x * 3 - win0;
+            const uint32_t* p = srct + rr * sw + (boff >> 2);
+            const int sh = (boff & 3) * 8;
+            const int4* k4 = reinterpret_cast<const int4*>(kxs + xx * ksx);
+            const int chunks = (b.y + 3) >> 2;
+            int a0 = half, a1 = half, a2 = half;
+            uint32_t w0 = p[0];
+            for (int c = 0; c < chunks; ++c) {
+                const uint32_t w1 = p[1], w2 = p[2], w3 = p[3];
+                const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
+                               v2 = __funnelshift_r(w2, w3, sh);
+                const int4 k = k4[c];
+                a0 += byte_of<0>(v0) * k.x + byte_of<3>(v0) * k.y + byte_of<2>(v1) * k.z + byte_of<1>(v2) * k.w;
+                a1 += byte_of<1>(v0) * k.x + byte_of<0>(v1) * k.y + byte_of<3>(v1) * k.z + byte_of<2>(v2) * k.w;
+                a2 += byte_of<2>(v0) * k.x + byte_of<1>(v1) * k.y + byte_of<0>(v2) * k.z + byte_of<3>(v2) * k.w;
+                w0 = w3;
+                p += 3;
+            }
+            tmp[rr * TMP_STRIDE + xx] = clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16);
+            xx += step_x;
+            rr += step_r;
+            if (rr >= nrows) { rr -= nrows; ++xx; }
         }
-        const int u0 = clip8(a0), u1 = clip8(a1), u2 = clip8(a2);
-        const int t_idx = (Y / tile) * tiles_x + (X / tile);
-        const int ly = Y % tile, lx = X % tile;
-        const size_t tile_id = static_cast<size_t>(f) * tiles_per_frame + tile_offset + t_idx;
-        const size_t plane = static_cast<size_t>(tile) * tile;
-        __nv_bfloat16* o = out + tile_id * 3 * plane + static_cast<size_t>(ly) * tile + lx;
-        o[0] = __float2bfloat16_rn(__ldg(lut + u0));
-        o[plane] = __float2bfloat16_rn(__ldg(lut + 256 + u1));
-        o[2 * plane] = __float2bfloat16_rn(__ldg(lut + 512 + u2));
+    }
+    __syncthreads();
+
+    // phase C: vertical taps, normalise, write bf16 NCHW (and optionally the uint8 HWC tile). Lane = column.
+    if (lane >= nx) return;
+    const int X = x0 + lane;
+    const int tcol = X / tile, lx = X - tcol * tile;
+    const size_t plane = static_cast<size_t>(tile) * tile;
+    int trow = y0 / tile, ly = y0 - trow * tile + warp;
+    for (int yy = warp; yy < ny; yy += 8, ly += 8) {
+        while (ly >= tile) { ly -= tile; ++trow; }
+        const int2 b = __ldg(by2 + yy);
+        const uint32_t* p = tmp + (b.x - ysrc0) * TMP_STRIDE + lane;
+        const int4* k4 = reinterpret_cast<const int4*>(kys + yy * ksy);
+        const int chunks = (b.y + 3) >> 2;
+        int a0 = half, a1 = half, a2 = half;
+        for (int c = 0; c < chunks; ++c) {
+            const int4 k = k4[c];
+            const uint32_t v0 = p[0], v1 = p[TMP_STRIDE], v2 = p[2 * TMP_STRIDE], v3 = p[3 * TMP_STRIDE];
+            a0 += byte_of<0>(v0) * k.x + byte_of<0>(v1) * k.y + byte_of<0>(v2) * k.z + byte_of<0>(v3) * k.w;
+            a1 += byte_of<1>(v0) * k.x + byte_of<1>(v1) * k.y + byte_of<1>(v2) * k.z + byte_of<1>(v3) * k.w;
+            a2 += byte_of<2>(v0) * k.x + byte_of<2>(v1) * k.y + byte_of<2>(v2) * k.z + byte_of<2>(v3) * k.w;
+            p += 4 * TMP_STRIDE;
+        }
+        const uint32_t u0 = clip8(a0), u1 = clip8(a1), u2 = clip8(a2);
+        const size_t tile_id = static_cast<size_t>(f) * tiles_per_frame + tile_offset + trow * tiles_x + tcol;
+        const size_t pix = static_cast<size_t>(ly) * tile + lx;
+        __nv_bfloat16* o = out + tile_id * 3 * plane + pix;
+        o[0] = lutb[u0];
+        o[plane] = lutb[256 + u1];
+        o[2 * plane] = lutb[512 + u2];
         if (tiles_u8) {
-            uint8_t* q = tiles_u8 + (tile_id * plane + static_cast<size_t>(ly) * tile + lx) * 3;
+            uint8_t* q = tiles_u8 + (tile_id * plane + pix) * 3;
             q[0] = static_cast<uint8_t>(u0);
             q[1] = static_cast<uint8_t>(u1);
             q[2] = static_cast<uint8_t>(u2);
@@ -149,20 +195,21 @@ double bicubic_filter(double x) {
 // When in_size == out_size Pillow skips the pass; an identity tap (1<<22) reproduces that bit-exactly.
 int plan_axis(int in_size, int out_size, std::vector<int32_t>& kk, std::vector<int32_t>& bounds) {
     if (in_size == out_size) {
-        kk.assign(out_size, 1 << PRECISION_BITS);
+        kk.assign(static_cast<size_t>(out_size) * 4, 0);
         bounds.resize(2 * static_cast<size_t>(out_size));
-        for (int i = 0; i < out_size; ++i) { bounds[2 * i] = i; bounds[2 * i + 1] = 1; }
-        return 1;
+        for (int i = 0; i < out_size; ++i) { kk[4 * i] = 1 << PRECISION_BITS; bounds[2 * i] = i; bounds[2 * i + 1] = 1; }
+        return 4;
     }
     const double in0 = 0.0, in1 = static_cast<double>(in_size);
     double scale, filterscale;
     filterscale = scale = (in1 - in0) / out_size;
     if (filterscale < 1.0) filterscale = 1.0;
     const double support = 2.0 * filterscale;
-    const int ksize = static_cast<int>(ceil(support)) * 2 + 1;
+    const int ksize_real = static_cast<int>(ceil(support)) * 2 + 1;
+    const int ksize = (ksize_real + 3) & ~3;  // row stride of the table: zero padded to whole 4-tap chunks
     kk.assign(static_cast<size_t>(out_size) * ksize, 0);
     bounds.resize(2 * static_cast<size_t>(out_size));
-    std::vector<double> w(ksize);
+    std::vector<double> w(ksize_real);
     const double ss = 1.0 / filterscale;
     for (int xx = 0; xx < out_size; ++xx) {
         const double center = in0 + (xx + 0.5) * scale;
@@ -188,51 +235,55 @@ int plan_axis(int in_size, int out_size, std::vector<int32_t>& kk, std::vector<i
     return ksize;
 }
 
-// Largest number of source rows any 32-row output block touches (sizes the shared-memory stage).
-int plan_max_rows(const std::vector<int32_t>& by, int out_h) {
-    int best = 1;
+// Shared-memory geometry of the kernel for one (source size, target size): the largest source window any 32x32 output
+// block touches, including the reach of the zero-padded taps.
+ResizeGeom plan_geometry(const std::vector<int32_t>& bx, const std::vector<int32_t>& by, int out_w, int out_h,
+                         int ksize_x, int ksize_y) {
+    ResizeGeom g{1, 1, 1};
     for (int y0 = 0; y0 < out_h; y0 += TY) {
         const int yl = (y0 + TY < out_h ? y0 + TY : out_h) - 1;
-        const int n = by[2 * yl] + by[2 * yl + 1] - by[2 * y0];
-        if (n > best) best = n;
+        g.rows_src = std::max(g.rows_src, by[2 * yl] + by[2 * yl + 1] - by[2 * y0]);
+        g.rows_tmp = std::max(g.rows_tmp, by[2 * yl] - by[2 * y0] + ksize_y);
     }
-    return best;
-}
-
-// Widest source window (in bytes, rounded for 4-byte staging) any 32-column output block touches.
-int plan_max_span_bytes(const std::vector<int32_t>& bx, int out_w) {
-    int best = 4;
+    g.rows_tmp = std::max(g.rows_tmp, g.rows_src);
     for (int x0 = 0; x0 < out_w; x0 += TX) {
         const int xl = (x0 + TX < out_w ? x0 + TX : out_w) - 1;
-        const int b0 = (bx[2 * x0] * 3) & ~3;
-        const int b1 = (bx[2 * xl] + bx[2 * xl + 1]) * 3;
-        const int n = ((b1 - b0 + 3) >> 2) << 2;
-        if (n > best) best = n;
+        const int win0 = (bx[2 * x0] * 3) & ~15;  // the most conservative window start the kernel uses
+        const int words = ((bx[2 * xl] * 3 - win0) >> 2) + 3 * (ksize_x >> 2) + 1;   // reach of the padded taps
+        g.span_words = std::max(g.span_words, words);
     }
-    return best + 4;
+    // whole 16-byte pieces plus one word: odd row stride (lanes on consecutive rows hit distinct banks) and room for
+    // the last piece phase A stores
+    g.span_words = ((g.span_words + 3) & ~3) + 1;
+    return g;
 }
 
-bool preprocess_fits(int max_rows, int span_bytes) {
-    return static_cast<size_t>(max_rows) * (TX * 3 + span_bytes) <= 200 * 1024;
+size_t preprocess_smem_bytes(const ResizeGeom& g, int ksize_x, int ksize_y) {
+    return static_cast<size_t>(TX) * ksize_x * 4 + static_cast<size_t>(TY) * ksize_y * 4 +
+           static_cast<size_t>(g.rows_src) * g.span_words * 4 + static_cast<size_t>(g.rows_tmp) * TMP_STRIDE * 4 + 768 * 2;
+}
+
+bool preprocess_fits(const ResizeGeom& g, int ksize_x, int ksize_y) {
+    return preprocess_smem_bytes(g, ksize_x, ksize_y) <= 200 * 1024;
 }
 
 cudaError_t launch_preprocess_impl(const uint8_t* frames, int n, int H, int W, int64_t frame_stride,
-                                   int64_t row_stride, const ResizePlan& plan, int max_rows, int span_bytes,
+                                   int64_t row_stride, const ResizePlan& plan, const ResizeGeom& geo,
                                    const float* lut, int tile, int tiles_x, int tiles_per_frame, int tile_offset,
                                    uint8_t* tiles_u8, __nv_bfloat16* out, cudaStream_t stream) {
-    const size_t smem = static_cast<size_t>(max_rows) * (TX * 3 + span_bytes);
+    const size_t smem = preprocess_smem_bytes(geo, plan.ksize_x, plan.ksize_y);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    const int aligned4 = ((reinterpret_cast<uintptr_t>(frames) | static_cast<uintptr_t>(frame_stride) |
-                           static_cast<uintptr_t>(row_stride)) & 3) == 0;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(frames) | static_cast<uintptr_t>(frame_stride) |
+                         static_cast<uintptr_t>(row_stride);
+    const int aligned = (al & 15) == 0 ? 2 : ((al & 3) == 0 ? 1 : 0);   // 2: 16-byte row loads, 1: words, 0: bytes
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              static_cast<int>(smem));
         if (e != cudaSuccess) return e;
     }
     dim3 grid((plan.out_w + TX - 1) / TX, (plan.out_h + TY - 1) / TY, n);
-    preprocess_kernel<<<grid, 256, smem, stream>>>(frames, H, W, frame_stride, row_stride, plan, lut, tile, tiles_x,
-                                                   tiles_per_frame, tile_offset, tiles_u8, out, max_rows, span_bytes,
-                                                   aligned4);
+    preprocess_kernel<<<grid, 256, smem, stream>>>(frames, W, frame_stride, row_stride, plan, lut, tile, tiles_x,
+                                                   tiles_per_frame, tile_offset, tiles_u8, out, geo, aligned);
     return cudaGetLastError();
 }
 

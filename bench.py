@@ -407,16 +407,18 @@ def run_native(args, rank, local_rank, world, out):
         for _ in range(2):
             eng.preprocess_frames(u8, max_num=1)
         torch.cuda.synchronize()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
+        eng.profile(True)   # kernel time from the library's CUDA events around each launch (the python call costs ~100 us)
+        eng.profile_read(reset=True)
         for _ in range(5):
             eng.preprocess_frames(u8, max_num=1)
-        p1.record()
         torch.cuda.synchronize()
-        pre_ms = p0.elapsed_time(p1) / 5
+        pre_ms = sum(v[0] for k, v in eng.profile_read(reset=True).items() if k.startswith("preprocess")) / 5
+        eng.profile(False)
         pre_bytes = nf * (fh * fw * 3 + 3 * cfg.image_size ** 2 * 2)
         bw["preprocess_u8"] = {"GBps": pre_bytes / pre_ms / 1e6, "bytes_per_frame": pre_bytes / nf,
-                               "frames_per_s": nf / pre_ms * 1e3, "source": f"{fh}x{fw} uint8 -> 448x448 bf16 tile"}
+                               "frames_per_s": nf / pre_ms * 1e3, "source": f"{fh}x{fw} uint8 -> 448x448 bf16 tile",
+                               "bound": "instruction issue (one PRMT + one IMAD per byte-tap of Pillow's 22-bit fixed-point "
+                                        "resampler), not HBM; see profiles/r2e_ncu_preprocess_summary.txt"}
         del u8
         M_rows = frames * cfg.tokens
         if "norm" in prof:
