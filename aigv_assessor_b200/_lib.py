@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaigv_b200.so")
 SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention2_tcgen05.cu", "rowops.cu", "preprocess.cu",
-           "llm_glue.cu"]
+           "llm_glue.cu", "llm_prefill.cu"]
 HEADERS = ["kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "aigv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-t", "0",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -90,6 +90,13 @@ class Cfg(C.Structure):
                 ("max_tiles", C.c_int32)]
 
 
+class LlmCfg(C.Structure):
+    _fields_ = [("hidden_size", C.c_int32), ("num_heads", C.c_int32), ("num_kv_heads", C.c_int32),
+                ("intermediate_size", C.c_int32), ("num_layers", C.c_int32), ("vocab_size", C.c_int32),
+                ("rms_norm_eps", C.c_float), ("rope_theta", C.c_float), ("max_tokens", C.c_int32),
+                ("max_positions", C.c_int32)]
+
+
 # name -> (restype, argtypes): exactly the symbols include/aigv_b200.h declares
 _P = C.c_void_p
 _F = C.POINTER(C.c_float)
@@ -124,6 +131,18 @@ SIGNATURES = {
     "aigv_exp2_poly": (C.c_int, [_P, _P, C.c_int, _P]),
     "aigv_splice_tokens": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
     "aigv_mlpscore": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_int, _P]),
+    "aigv_llm_create": (C.c_int, [C.POINTER(LlmCfg), C.POINTER(_P)]),
+    "aigv_llm_destroy": (None, [_P]),
+    "aigv_llm_last_error": (C.c_char_p, [_P]),
+    "aigv_llm_launch_count": (C.c_int64, [_P]),
+    "aigv_llm_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "aigv_llm_finalize_weights": (C.c_int, [_P, _P]),
+    "aigv_llm_prefill": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "aigv_llm_hidden_rows": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, _P, _P]),
+    "aigv_llm_logits_rows": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, _P, _P]),
+    "aigv_llm_copy_residual": (C.c_int, [_P, _P, _P]),
+    "aigv_rope": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "aigv_attention_gqa": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "aigv_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "aigv_rmsnorm_inplace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_im2col": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

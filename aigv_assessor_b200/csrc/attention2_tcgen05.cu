@@ -104,15 +104,24 @@ struct Geo2 {
 };
 
 struct Item {
-    int frame, head, q0, row_base, n_t;
+    int frame, head, q0, row_base, n_t, n_b;
     bool side;
 };
+
+// Where q / k / v of head h live in a row of the fused projection output (see AttnLayout in kernels.h).
+__device__ __forceinline__ int col_q(const AttnLayout& L, int h, int HD) {
+    return (h / L.q_group) * L.grp_stride + (h % L.q_group) * HD;
+}
+__device__ __forceinline__ int col_k(const AttnLayout& L, int h) {
+    return (h / L.q_group) * L.grp_stride + L.k_off + (h % L.q_group) * L.k_mul;
+}
 
 // item index -> (frame, head, chunk). Items of one (frame, head) are adjacent (their CTAs share K/V in L2); the chunk is
 // rotated by the pass number so the CTA that gets the class-token row changes from pass to pass. s_rows = rows that
 // tiles cover (the sequence without the class-token side row).
-template <int CHUNK, int TILES>
-__device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, int H, int S, int s_rows, bool side_mode) {
+template <int CHUNK, int TILES, int BKV>
+__device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, int H, int S, int s_rows, bool side_mode,
+                                            int n_blocks, bool causal) {
     Item m;
     const int fh = i / n_chunks;
     const int raw = i - fh * n_chunks;
@@ -124,6 +133,8 @@ __device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, in
     const int left = s_rows - m.q0;
     m.n_t = left >= CHUNK ? TILES : (left + BQ - 1) / BQ;
     m.side = side_mode && chunk == 0;
+    // causal: keys up to the item's last query row only (blocks past a tile's own diagonal are masked, not skipped)
+    m.n_b = causal ? min(n_blocks, (min(m.q0 + m.n_t * BQ, S) + BKV - 1) / BKV) : n_blocks;
     return m;
 }
 
@@ -166,11 +177,11 @@ __device__ __forceinline__ void exp2_poly2(f32x2 x, float& p0, float& p1) {
     p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-template <int HD>
+template <int HD, bool kCausal>
 __global__ void __launch_bounds__(Geo2<HD>::THREADS, 1)
 attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                       const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int H, int n_items,
-                      int n_chunks, int rot_div, int side_mode, float scale_log2) {
+                      int n_chunks, int rot_div, int side_mode, float scale_log2, const AttnLayout lay) {
     using G = Geo2<HD>;
     constexpr int TILES = G::TILES, BKV = G::BKV, CHUNK = G::CHUNK, SOFTMAX_WARPS = G::SOFTMAX_WARPS,
                   WARP_PRODUCER = G::WARP_PRODUCER, WARP_MMA = G::WARP_MMA, WARP_SIDE = G::WARP_SIDE, KPW = G::KPW;
@@ -207,7 +218,8 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     const int lane = threadIdx.x & 31;
     const int n_full = S / BKV;
     const int tail_valid = S - n_full * BKV;
-    const bool tail_epi = tail_valid == 1 && n_full >= 1;
+    constexpr bool causal = kCausal;  // a compile-time variant: the bidirectional (ViT) instantiation carries none of it
+    const bool tail_epi = tail_valid == 1 && n_full >= 1 && !causal;
     const int n_blocks = n_full + ((tail_valid > 0 && !tail_epi) ? 1 : 0);
     const bool smode = side_mode != 0;
     const int s_rows = S - (smode ? 1 : 0);  // query rows that tiles cover
@@ -255,54 +267,63 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             int it = 0;
             uint32_t kst = 0, kph = 0;  // K/V ring position of the next block to load
             for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++it) {
-                const Item m = decode_item<CHUNK, TILES>(i, n_chunks, rot_div, H, S, s_rows, smode);
+                const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
                 const int qb = it % QBUFS;
-                auto load_kv = [&](int j) {
+                auto load_k = [&](int j) {
                     const int r = m.row_base + j * BKV;
                     mbar_wait(&k_empty[kst], kph ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&k_full[kst], KV_BYTES);
                         for (int a = 0; a < ATOMS; ++a)
                             tma_load_2d(smem + OFF_K + kst * KV_BYTES + a * KV_ATOM, &tm_kv, &k_full[kst],
-                                        H * HD + m.head * HD + a * 64, r);
+                                        col_k(lay, m.head) + a * 64, r);
                     }
                     __syncwarp();
+                };
+                auto load_v = [&](int j) {   // also advances the ring
+                    const int r = m.row_base + j * BKV;
                     mbar_wait(&v_empty[kst], kph ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&v_full[kst], KV_BYTES);
                         for (int a = 0; a < ATOMS; ++a)
                             tma_load_2d(smem + OFF_V + kst * KV_BYTES + a * KV_ATOM, &tm_kv, &v_full[kst],
-                                        2 * H * HD + m.head * HD + a * 64, r);
+                                        col_k(lay, m.head) + lay.v_off + a * 64, r);
                     }
                     __syncwarp();
                     if (++kst == static_cast<uint32_t>(STAGES)) { kst = 0; kph ^= 1; }
                 };
-                // With a single Q buffer the Q tiles can only land after the previous item's last Q K^T: have the
-                // first K/V block in flight before waiting for that.
-                int j0 = 0;
-                if (QBUFS == 1 && STAGES >= 2) { load_kv(0); j0 = 1; }
+                // With a single Q buffer the Q tiles can only land after the previous item's last Q K^T: have the first K
+                // block in flight before waiting for that. Only K: the V stage it would take is released by a P V of the
+                // previous item that the MMA warp issues together with THIS item's first Q K^T when that item had a single
+                // live tile (Q K^T then runs two blocks ahead), i.e. only after these Q tiles have landed -- waiting for
+                // that V stage before loading Q deadlocks (found by the first multi-item run with ragged 128-wide heads).
+                const bool early_k = QBUFS == 1 && STAGES >= 2;
+                if (early_k) load_k(0);
                 mbar_wait(&q_empty[qb], ((it / QBUFS) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&q_full[qb], m.n_t * Q_BYTES);
                     for (int t = 0; t < m.n_t; ++t)
                         for (int a = 0; a < ATOMS; ++a)
                             tma_load_2d(smem + OFF_Q + (qb * TILES + t) * Q_BYTES + a * Q_ATOM, &tm_q, &q_full[qb],
-                                        m.head * HD + a * 64, m.row_base + m.q0 + t * BQ);
+                                        col_q(lay, m.head, HD) + a * 64, m.row_base + m.q0 + t * BQ);
                 }
                 __syncwarp();
                 if (tail_epi) {
                     float* kt = kt_ring + (it & 1) * 2 * HD;
                     const __nv_bfloat16* kg =
-                        qkv + static_cast<size_t>(m.row_base + S - 1) * (3 * H * HD) + H * HD + m.head * HD;
+                        qkv + static_cast<size_t>(m.row_base + S - 1) * lay.row_pitch + col_k(lay, m.head);
 #pragma unroll
                     for (int e = 0; e < DPL; ++e) {
                         kt[lane * DPL + e] = __bfloat162float(kg[lane * DPL + e]);
-                        kt[HD + lane * DPL + e] = __bfloat162float(kg[H * HD + lane * DPL + e]);
+                        kt[HD + lane * DPL + e] = __bfloat162float(kg[lay.v_off + lane * DPL + e]);
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&q_full[qb]);
-                for (int j = j0; j < n_blocks; ++j) load_kv(j);
+                for (int j = 0; j < m.n_b; ++j) {
+                    if (j > 0 || !early_k) load_k(j);
+                    load_v(j);
+                }
             }
         } else if (warp == WARP_MMA) {
             // ------------------------------------------------------------ MMA issuer
@@ -318,17 +339,22 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const int my_items = (n_items > static_cast<int>(blockIdx.x))
                                      ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                                      : 0;
-            const bool uniform_nt = (s_rows % CHUNK) == 0;  // every item has all its tiles live
-            auto nt_of = [&](int it) -> int {
-                if (uniform_nt) return TILES;
-                return decode_item<CHUNK, TILES>(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x), n_chunks,
-                                                 rot_div, H, S, s_rows, smode).n_t;
+            const bool uniform = (s_rows % CHUNK) == 0 && !causal;  // every item: all tiles live, all key blocks
+            // (live tiles, key blocks) of this CTA's it-th item
+            auto geom_of = [&](int it, int& nt, int& nb) {
+                if (it >= my_items) { nt = 0; nb = n_blocks; return; }
+                if (uniform) { nt = TILES; nb = n_blocks; return; }
+                const Item m = decode_item<CHUNK, TILES, BKV>(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x),
+                                                              n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
+                nt = m.n_t;
+                nb = m.n_b;
             };
             // Q K^T cursor
-            int q_it = 0, q_j = 0, q_t = 0, q_nt = my_items ? nt_of(0) : 0;
+            int q_it = 0, q_j = 0, q_t = 0, q_nt, q_nb;
+            geom_of(0, q_nt, q_nb);
             uint32_t q_b = 0, q_kst = 0, q_kph = 0, q_qb = 0, q_qph = 0;
             // P V cursor
-            int p_it = 0, p_j = 0, p_t = 0, p_nt = q_nt;
+            int p_it = 0, p_j = 0, p_t = 0, p_nt = q_nt, p_nb = q_nb;
             uint32_t p_b = 0, p_bph = 0, p_vst = 0, p_vph = 0;
             uint32_t pv_cnt[TILES];  // P V steps issued per tile: slot of the tile's pv_done ring = count % PVR
 #pragma unroll
@@ -343,8 +369,8 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                     mbar_wait(&k_full[q_kst], q_kph);
                 }
                 tc_fence_after();
-                const bool p_last_t = p_t == p_nt - 1, p_last_j = p_j == n_blocks - 1;
-                const bool q_last_t = q_t == q_nt - 1, q_last_j = q_j == n_blocks - 1;
+                const bool p_last_t = p_t == p_nt - 1, p_last_j = p_j == p_nb - 1;
+                const bool q_last_t = q_t == q_nt - 1, q_last_j = q_j == q_nb - 1;
                 const uint64_t vd = v_desc0 + ((p_vst * static_cast<uint32_t>(KV_BYTES)) >> 4);
                 const uint32_t tm_p = tmem_u + p_b * BKV;  // bf16 pairs in the first BKV/2 columns of the S buffer
                 const uint32_t tm_o = tmem_u + TM_O + p_t * HD;
@@ -389,7 +415,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                         if (p_last_j) {
                             p_j = 0;
                             ++p_it;
-                            p_nt = p_it < my_items ? nt_of(p_it) : 0;
+                            geom_of(p_it, p_nt, p_nb);
                         } else {
                             ++p_j;
                         }
@@ -406,7 +432,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                             q_j = 0;
                             ++q_it;
                             if (++q_qb == static_cast<uint32_t>(QBUFS)) { q_qb = 0; q_qph ^= 1; }
-                            q_nt = q_it < my_items ? nt_of(q_it) : 0;
+                            geom_of(q_it, q_nt, q_nb);
                         } else {
                             ++q_j;
                         }
@@ -430,17 +456,17 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             float* ps = p_side + w * KPW;
             uint32_t kst = 0, kph = 0;
             for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
-                const Item m = decode_item<CHUNK, TILES>(i, n_chunks, rot_div, H, S, s_rows, smode);
+                const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
                 float m_run = -INFINITY, l_lane = 0.f, o_acc[DPL];
 #pragma unroll
                 for (int e = 0; e < DPL; ++e) o_acc[e] = 0.f;
-                const __nv_bfloat16* qg = qkv + static_cast<size_t>(m.row_base + S - 1) * (3 * H * HD) + m.head * HD;
+                const __nv_bfloat16* qg = qkv + static_cast<size_t>(m.row_base + S - 1) * lay.row_pitch + col_q(lay, m.head, HD);
                 if (m.side) {
 #pragma unroll
                     for (int e = 0; e < DPL; ++e) qs[lane * DPL + e] = __bfloat162float(qg[lane * DPL + e]) * scale_log2;
                     __syncwarp();
                 }
-                for (int j = 0; j < n_blocks; ++j) {
+                for (int j = 0; j < m.n_b; ++j) {
                     mbar_wait(&k_full[kst], kph);
                     float corr = 1.f;
                     if (m.side) {  // side mode: every block is full (S = 128 k + 1, the tail key is folded at the end)
@@ -524,12 +550,13 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
                         for (int e = 0; e < DPL; ++e) o_acc[e] = o_acc[e] * a0 + merge[lane * DPL + e] * a1;
                         if (tail_epi) {  // the lone tail key: one more online-softmax step, dims spread over the lanes
-                            const __nv_bfloat16* kg = qg + H * HD;
+                            const __nv_bfloat16* kg =
+                                qkv + static_cast<size_t>(m.row_base + S - 1) * lay.row_pitch + col_k(lay, m.head);
                             float stl = 0.f, vt[DPL];
 #pragma unroll
                             for (int e = 0; e < DPL; ++e) {
                                 stl = fmaf(qs[lane * DPL + e], __bfloat162float(kg[lane * DPL + e]), stl);
-                                vt[e] = __bfloat162float(kg[H * HD + lane * DPL + e]);
+                                vt[e] = __bfloat162float(kg[lay.v_off + lane * DPL + e]);
                             }
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) stl += __shfl_xor_sync(0xffffffffu, stl, o);
@@ -572,7 +599,7 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         };
         advance_sb(t);  // tile t's first step is step t of the sequence (when all tiles are live; see below)
         for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++it) {
-            const Item m = decode_item<CHUNK, TILES>(i, n_chunks, rot_div, H, S, s_rows, smode);
+            const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
             const int qb = it % QBUFS;
             const uint32_t qph = (it / QBUFS) & 1;
             // Step index of (block j, tile t) inside this item is j * n_t + t: sb/sph were positioned for tile t with all
@@ -580,9 +607,9 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             if (t >= m.n_t) {  // this warpgroup's tile holds no query row: only release Q (and keep passing the turn)
                 mbar_wait(&q_full[qb], qph);
                 if (lane == 0) mbar_arrive(&q_empty[qb]);
-                advance_sb(static_cast<uint32_t>(n_blocks * m.n_t));
+                advance_sb(static_cast<uint32_t>(m.n_b * m.n_t));
                 if (AIGV_ATTN_PINGPONG)
-                    for (int j = 0; j < n_blocks; ++j) {
+                    for (int j = 0; j < m.n_b; ++j) {
                         named_bar_sync(pp_mine, 64);
                         named_bar_arrive(pp_next, 64);
                     }
@@ -609,10 +636,12 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 #pragma unroll
                     for (int c = 0; c < BKV; c += 32) tmem_ld_32x32(tm_s + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
                     tmem_ld_wait();
-                    if (kMasked) {  // masked tail block (never taken for ViT sequences)
+                    if (kMasked) {  // ragged tail block / causal diagonal and beyond (never taken for ViT sequences)
+                        // keys of this block the row may attend to: all that exist, or those up to its own position
+                        const int valid = causal ? tile_q0 + r - j * BKV + 1 : tail_valid;
 #pragma unroll
                         for (int c = 0; c < BKV; ++c)
-                            if (c >= tail_valid) v[c] = 0xff800000u;
+                            if (c >= valid) v[c] = 0xff800000u;
                     }
                     float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -716,9 +745,12 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 }
             };
             {
+                // blocks [0, jm) need no mask for any row of this warp: whole blocks of existing keys, and (causal) ending
+                // at or before the warp's first query row
+                const int jm = causal ? min(m.n_b, (tile_q0 + wq * 32 + 1) / BKV) : min(n_full, m.n_b);
                 int j = 0;
-                for (; j < n_full; ++j) softmax_block(j, std::false_type{});
-                if (j < n_blocks) softmax_block(j, std::true_type{});
+                for (; j < jm; ++j) softmax_block(j, std::false_type{});
+                for (; j < m.n_b; ++j) softmax_block(j, std::true_type{});
             }
 
             // epilogue: fold the lone tail key in (exact reference update), normalise, store
@@ -789,13 +821,14 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 template <int HD>
 cudaError_t launch_attention2_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const __nv_bfloat16* qkv,
                                  __nv_bfloat16* out, int frames, int S, int heads, float softmax_scale, int num_sms,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, const AttnLayout& lay) {
     using G = Geo2<HD>;
-    static unsigned long long optin_mask = 0;
-    cudaError_t e = ensure_smem_optin(reinterpret_cast<const void*>(&attention_fwd2_kernel<HD>), G::SMEM_BYTES, optin_mask);
+    static unsigned long long optin_mask[2] = {0, 0};
+    auto kernel = lay.causal ? &attention_fwd2_kernel<HD, true> : &attention_fwd2_kernel<HD, false>;
+    cudaError_t e = ensure_smem_optin(reinterpret_cast<const void*>(kernel), G::SMEM_BYTES, optin_mask[lay.causal ? 1 : 0]);
     if (e != cudaSuccess) return e;
     // side mode: S = k * 128 + 1 (k >= 1) -- the leftover query row rides on the side warps of the first chunk
-    const int side_mode = (S > BQ && S % BQ == 1 && qkv != nullptr) ? 1 : 0;
+    const int side_mode = (S > BQ && S % BQ == 1 && qkv != nullptr && !lay.causal) ? 1 : 0;
     const int s_rows = S - side_mode;
     const int n_chunks = (s_rows + G::CHUNK - 1) / G::CHUNK;
     const long long n_items = static_cast<long long>(frames) * heads * n_chunks;
@@ -805,8 +838,8 @@ cudaError_t launch_attention2_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_
     int rot_div = grid / n_chunks;
     if (rot_div < 1) rot_div = 1;
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    attention_fwd2_kernel<HD><<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(
-        tm_q, tm_kv, qkv, out, S, heads, static_cast<int>(n_items), n_chunks, rot_div, side_mode, scale_log2);
+    kernel<<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(
+        tm_q, tm_kv, qkv, out, S, heads, static_cast<int>(n_items), n_chunks, rot_div, side_mode, scale_log2, lay);
     return cudaGetLastError();
 }
 
@@ -833,10 +866,14 @@ int attention2_kv_box_rows(int head_dim) { return head_dim == 64 ? Geo2<64>::BKV
 
 cudaError_t launch_attention2(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const __nv_bfloat16* qkv,
                               __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
-                              int num_sms, cudaStream_t stream) {
+                              int num_sms, cudaStream_t stream, const AttnLayout* layout) {
     if (frames <= 0 || S <= 0 || heads <= 0) return cudaErrorInvalidValue;
-    if (head_dim == 64) return launch_attention2_hd<64>(tm_q, tm_kv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream);
-    if (head_dim == 128) return launch_attention2_hd<128>(tm_q, tm_kv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream);
+    // default: the ViT's fused qkv output, channel order (three, head, d), bidirectional
+    AttnLayout lay{3 * heads * head_dim, heads, 0, heads * head_dim, head_dim, heads * head_dim, 0};
+    if (layout) lay = *layout;
+    if (lay.q_group <= 0 || heads % lay.q_group != 0) return cudaErrorInvalidValue;
+    if (head_dim == 64) return launch_attention2_hd<64>(tm_q, tm_kv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream, lay);
+    if (head_dim == 128) return launch_attention2_hd<128>(tm_q, tm_kv, qkv, out, frames, S, heads, softmax_scale, num_sms, stream, lay);
     return cudaErrorInvalidValue;
 }
 

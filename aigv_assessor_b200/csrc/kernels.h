@@ -60,9 +60,19 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 // persistent CTAs to launch.
 int attention2_q_box_rows();
 int attention2_kv_box_rows(int head_dim);
+// Where head h's q / k / v columns sit in a row of the fused projection output, and the mask:
+//   q at (h / q_group) * grp_stride + (h % q_group) * head_dim
+//   k at (h / q_group) * grp_stride + k_off + (h % q_group) * k_mul,   v at k + v_off
+// ViT qkv (three, head, d):            {3*H*d, H, 0, H*d, d, H*d, 0}
+// InternLM2 wqkv (kv group, G q + k + v, d), G = heads / kv heads (modeling_internlm2.py:373-389), causal:
+//                                       {(H + 2*Hkv)*d, G, (G+2)*d, G*d, 0, d, 1}
+struct AttnLayout {
+    int row_pitch, q_group, grp_stride, k_off, k_mul, v_off, causal;
+};
+// layout == nullptr: the ViT layout above. causal: key <= query position inside each sequence of S rows.
 cudaError_t launch_attention2(const CUtensorMap& tm_q, const CUtensorMap& tm_kv, const __nv_bfloat16* qkv,
                               __nv_bfloat16* out, int frames, int S, int heads, int head_dim, float softmax_scale,
-                              int num_sms, cudaStream_t stream);
+                              int num_sms, cudaStream_t stream, const AttnLayout* layout = nullptr);
 
 // Test hook: y[i] = the attention kernel's FMA-pipe 2^x (exp2_poly2) for x[i] (softmax arguments are <= 8).
 cudaError_t launch_exp2_poly_test(const float* x, float* y, int n, cudaStream_t stream);

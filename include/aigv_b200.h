@@ -157,6 +157,61 @@ int aigv_assemble_tokens(const float* pe, const float* cls, const float* pos, fl
 int aigv_pixel_shuffle(const float* x, const float* w, const float* b, void* y_bf16, int n, int g, int D, float eps,
                        int apply_ln, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Above the seam, second piece: the InternLM2 prefill of the stage-2 forward
+ *   outputs = self.language_model(inputs_embeds=input_embeds, ..., output_hidden_states=True)
+ *   (/root/reference/internvl/model/internvl_chat_eval2/modeling_internvl_chat.py:441-450 ->
+ *    /root/reference/internvl/model/internlm2/modeling_internlm2.py:1036-1124 -> :868-998 -> :635-695)
+ * of which the caller consumes hidden_states[-1][:, -4] (mlpscore, eval2 :469-475) and the argmax of the answer-span
+ * logits (eval2 :488, stage1_eval.py:928-929). One handle = one InternLM2 decoder stack on the current device.
+ * Scope: a full prefill of B unpadded prompts of N tokens each (positions 0..N-1, causal mask), bf16 with fp32 accumulation
+ * and an fp32 residual stream; no KV cache / decode, no padding mask, N <= max_positions (LLM:218-244 dynamic NTK leaves the
+ * rotary base unchanged there). */
+typedef struct aigv_llm_handle aigv_llm_handle;
+
+/* Mirrors the InternLM2Config fields the prefill reads (configuration_internlm2.py). */
+typedef struct aigv_llm_cfg {
+    int32_t hidden_size;
+    int32_t num_heads;
+    int32_t num_kv_heads;
+    int32_t intermediate_size;
+    int32_t num_layers;
+    int32_t vocab_size;
+    float rms_norm_eps;
+    float rope_theta;
+    int32_t max_tokens;     /* workspace: tokens (B*N) per aigv_llm_prefill call */
+    int32_t max_positions;  /* max_position_embeddings; longer prompts are refused (0 = do not check) */
+} aigv_llm_cfg;
+
+int aigv_llm_create(const aigv_llm_cfg* cfg, aigv_llm_handle** out);
+void aigv_llm_destroy(aigv_llm_handle* h);
+const char* aigv_llm_last_error(const aigv_llm_handle* h);
+int64_t aigv_llm_launch_count(const aigv_llm_handle* h);
+/* `name` is the reference state-dict key, with or without the "language_model." prefix:
+ * model.layers.{i}.attention.wqkv.weight / .attention.wo.weight / .attention_norm.weight / .ffn_norm.weight /
+ * .feed_forward.w1.weight / .w2.weight / .w3.weight, model.norm.weight, output.weight (optional: only aigv_llm_logits_rows
+ * needs it). Host or device pointer, fp32 or bf16; copied and re-packed (RMSNorm weights folded into wqkv / w1 / w3, w1 and
+ * w3 interleaved). Synchronous. */
+int aigv_llm_set_weight(aigv_llm_handle* h, const char* name, const void* ptr, int dtype, const int64_t* shape, int rank);
+int aigv_llm_finalize_weights(aigv_llm_handle* h, void* stream);
+/* The decoder stack on inputs_embeds bf16 [B*N, hidden] (sample-major; = the output of aigv_splice_tokens). The residual
+ * stream of the last layer stays in the handle for the two readers below. Asynchronous on `stream`. */
+int aigv_llm_prefill(aigv_llm_handle* h, const void* inputs_embeds_bf16, int B, int N, void* stream);
+/* hidden_states[-1] (= final RMSNorm applied, modeling_internlm2.py:984) of the given flattened rows b*N + pos of the last
+ * prefill -> out fp32 [n, hidden]. rows is a HOST array (n <= 512). */
+int aigv_llm_hidden_rows(aigv_llm_handle* h, const int32_t* rows_host, int n, float* out_f32, void* stream);
+/* logits (output head, modeling_internlm2.py:1095) of the given rows only -> out fp32 [n, vocab_size]. */
+int aigv_llm_logits_rows(aigv_llm_handle* h, const int32_t* rows_host, int n, float* out_f32, void* stream);
+/* Debug/test: the fp32 residual stream [B*N, hidden] after the last layer, before the final norm. */
+int aigv_llm_copy_residual(aigv_llm_handle* h, float* dst, void* stream);
+/* Per-op entry points of the prefill (tests). qkv bf16 [B*N, (heads + 2*kv_heads)*head_dim] in InternLM2's wqkv packing
+ * (kv group, G query heads + k + v, d) (modeling_internlm2.py:373-389). aigv_rope rotates its q and k columns in place
+ * (:247-260, positions 0..N-1; synchronous); aigv_attention_gqa -> out bf16 [B*N, heads*head_dim] with K / V shared per
+ * group (:404-405) and, if causal, key <= query position (:411-416 mask). */
+int aigv_rope(void* qkv_bf16, int B, int N, int heads, int kv_heads, int head_dim, float theta, void* stream);
+int aigv_attention_gqa(const void* qkv_bf16, void* out_bf16, int B, int N, int heads, int kv_heads, int head_dim,
+                       float scale, int causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,10 @@ def _attn_ref(qkv, frames, S, H, d):
                                           # round-2 kernel: any tail, dead second tiles, several items per persistent CTA
                                           (2, 100, 2, 64), (1, 300, 2, 64), (1, 640, 1, 64), (1, 1, 2, 64), (2, 129, 1, 64),
                                           (3, 384, 2, 128), (4, 1025, 16, 64), (5, 513, 16, 64), (2, 1025, 25, 128),
-                                          (37, 200, 5, 64)])
+                                          (37, 200, 5, 64),
+                                          # several items per CTA where a single-live-tile item is followed by another one
+                                          # (128-wide heads have ONE Q buffer: the producer's early K/V load deadlocked there)
+                                          (4, 300, 25, 128), (3, 2108, 32, 128), (8, 300, 16, 64)])
 def test_attention_matches_reference(frames, S, H, d):
     g = torch.Generator().manual_seed(S + H + d)
     qkv = (torch.randn((frames * S, 3 * H * d), generator=g) * (1.5 if d == 64 else 1.2)).to(torch.bfloat16)

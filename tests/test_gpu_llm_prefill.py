@@ -1,0 +1,177 @@
+"""SURVEY 8f next-1, second piece: the InternLM2 prefill as CUDA kernels (rotary embedding, causal grouped-query attention
+on tcgen05, RMSNorm-fused wqkv / w1|w3 GEMMs, SwiGLU, fused-residual wo / w2, final norm + output head on selected rows)
+against oracle/head_oracle.py, which tests/test_oracle_golden.py pins to the unmodified reference forward."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from aigv_assessor_b200 import llm as L
+from aigv_assessor_b200 import llm_glue, synth
+from oracle import head_oracle as ho
+from oracle import vit_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+
+def _qkv(B, N, nh, nkv, hd, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn((B * N, (nh + 2 * nkv) * hd), generator=g) * scale).to(torch.bfloat16)
+
+
+def _split(qkv, B, N, nh, nkv, hd):
+    """InternLM2's rearrange (modeling_internlm2.py:375-389): -> q [B,nh,N,hd], k/v [B,nkv,N,hd] (fp32)."""
+    G = nh // nkv
+    t = qkv.float().view(B, N, nkv, G + 2, hd)
+    q = t[..., :G, :].reshape(B, N, nh, hd).transpose(1, 2)
+    return q, t[..., -2, :].transpose(1, 2), t[..., -1, :].transpose(1, 2)
+
+
+def _ref_attention(qkv, B, N, nh, nkv, hd, causal):
+    q, k, v = _split(qkv, B, N, nh, nkv, hd)
+    G = nh // nkv
+    k = k[:, :, None].expand(B, nkv, G, N, hd).reshape(B, nh, N, hd)
+    v = v[:, :, None].expand(B, nkv, G, N, hd).reshape(B, nh, N, hd)
+    a = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd)
+    if causal:
+        a = a + torch.full((N, N), float("-inf")).triu(1)
+    return torch.matmul(F.softmax(a, dim=-1), v).transpose(1, 2).reshape(B * N, nh * hd)
+
+
+@pytest.mark.parametrize("B,N,nh,nkv,hd", [(1, 1, 2, 1, 64), (2, 100, 4, 2, 64), (1, 128, 2, 2, 128), (1, 129, 4, 1, 128),
+                                           (2, 300, 8, 2, 128), (1, 513, 4, 2, 64), (1, 2108, 8, 2, 128),
+                                           # more work items than persistent CTAs (the shape of the 7B prefill) / two prompts
+                                           (1, 2108, 32, 8, 128), (2, 1100, 16, 8, 128), (3, 700, 16, 8, 64)])
+@pytest.mark.parametrize("causal", [True, False])
+def test_gqa_attention_matches_fp32_softmax(B, N, nh, nkv, hd, causal):
+    qkv = _qkv(B, N, nh, nkv, hd, seed=N + nh)
+    out = L.attention_gqa(qkv.cuda(), B, N, nh, nkv, hd, causal=causal)
+    torch.cuda.synchronize()
+    ref = _ref_attention(qkv, B, N, nh, nkv, hd, causal)
+    err = float((out.float().cpu() - ref).abs().max() / ref.abs().max())
+    assert torch.isfinite(out.float()).all()
+    assert err < 1.2e-2, err   # bf16 P and bf16 output against an fp32 softmax
+
+
+def test_causal_attention_peaked_scores_and_first_rows():
+    """Large logits (forced rescales of the stale maximum) and the rows that see one / two keys."""
+    B, N, nh, nkv, hd = 1, 400, 4, 2, 128
+    qkv = _qkv(B, N, nh, nkv, hd, seed=9, scale=3.0)
+    out = L.attention_gqa(qkv.cuda(), B, N, nh, nkv, hd, causal=True).float().cpu()
+    ref = _ref_attention(qkv, B, N, nh, nkv, hd, True)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1.5e-2
+    _, _, v = _split(qkv, B, N, nh, nkv, hd)
+    # row 0 attends to key 0 only: the output is exactly v[0] of its kv group
+    v0 = v[0, :, 0, :].repeat_interleave(nh // nkv, dim=0).reshape(-1)
+    assert torch.equal(out[0], v0)
+
+
+@pytest.mark.parametrize("B,N,nh,nkv,hd", [(2, 77, 4, 2, 128), (1, 300, 4, 4, 64)])
+def test_rope_matches_the_rotate_half_form(B, N, nh, nkv, hd):
+    theta = 1e6
+    qkv = _qkv(B, N, nh, nkv, hd, seed=3)
+    out = L.rope_(qkv.clone().cuda(), B, N, nh, nkv, hd, theta).float().cpu()
+    q, k, v = _split(qkv, B, N, nh, nkv, hd)
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2).float() / hd))
+    fr = torch.einsum("i,j->ij", torch.arange(N).float(), inv)
+    emb = torch.cat((fr, fr), dim=-1)
+    cos, sin = emb.cos()[None, None], emb.sin()[None, None]
+    rq = q * cos + ho._rotate_half(q) * sin
+    rk = k * cos + ho._rotate_half(k) * sin
+    oq, ok, ov = _split(out, B, N, nh, nkv, hd)
+    assert torch.equal(ov, v)                                      # v untouched
+    assert float((oq - rq).abs().max()) < 2e-2 * float(rq.abs().max())   # one bf16 rounding of an O(4) value
+    assert float((ok - rk).abs().max()) < 2e-2 * float(rk.abs().max())
+    assert float((oq - rq).abs().mean()) < 2e-3 * float(rq.abs().max())
+
+
+def _head_case(golden_dir, name="tiny"):
+    with open(os.path.join(golden_dir, "golden_meta_full.json")) as f:
+        meta = json.load(f)[name]
+    sd_head = synth.make_head_weights(seed=meta["seeds"]["head"])
+    sd_head["mlpscore.fc5.weight"] = synth.bf16_round(sd_head["mlpscore.fc5.weight"] * np.float32(meta["fc5_scale"]))
+    return meta, sd_head, np.load(os.path.join(golden_dir, f"full_{name}.npz"))
+
+
+def test_prefill_matches_the_oracle_on_random_embeddings(golden_dir):
+    """Two prompts of 300 tokens through the 2-layer 4096-wide InternLM2 of the goldens: residual stream, final-norm rows and
+    logits against the fp32 oracle on the same bf16 inputs."""
+    meta, sd_head, _ = _head_case(golden_dir)
+    llm = meta["llm"]
+    sdt = ho.to_torch(sd_head)
+    g = torch.Generator().manual_seed(17)
+    B, N = 2, 300
+    emb = (torch.randn((B, N, llm["hidden_size"]), generator=g) * 0.5).to(torch.bfloat16)
+    eng = L.LanguageEngine(llm, max_tokens=B * N).load_state_dict(sd_head)
+    eng.prefill(emb.cuda())
+    rows = [N - 4, N - 1, N + 5, 2 * N - 4]
+    hid = eng.hidden_rows(rows).cpu()
+    logits = eng.logits_rows(rows).cpu()
+    torch.cuda.synchronize()
+    ref_h, ref_l = ho.internlm2(emb.float(), sdt, llm)
+    ref_h, ref_l = ref_h.reshape(B * N, -1)[rows], ref_l.reshape(B * N, -1)[rows]
+    e_h = vo.error_metrics(hid.numpy(), ref_h.numpy())
+    e_l = vo.error_metrics(logits.numpy(), ref_l.numpy())
+    print(f"prefill vs oracle: hidden rows e_max/e_l2 {e_h}  logits {e_l}")
+    assert e_h[0] < 2e-2 and e_l[0] < 2e-2
+    assert eng.launch_count >= 1 + 7 * llm["num_hidden_layers"]
+
+
+def test_score_with_everything_on_the_gpu(golden_dir):
+    """The whole stage-2 forward on the GPU -- CUDA visual tokens -> CUDA splice -> CUDA InternLM2 prefill -> CUDA mlpscore and
+    output head -- against the reference's own score1 / answer-span argmax (north_star: 0.02 absolute). Only the SlowFast
+    stand-in and motion_mlp (one 2304-vector per clip) stay on the host."""
+    from aigv_assessor_b200.config import VisionPathConfig
+    from aigv_assessor_b200.engine import VisionEngine
+    meta, sd_head, g = _head_case(golden_dir)
+    llm = meta["llm"]
+    cfg = VisionPathConfig(**meta["vis_cfg"])
+    sd_vis = synth.make_weights(cfg, seed=meta["seeds"]["vis"])
+    pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["seeds"]["x"])
+    ids = synth.make_clip_prompt(meta["n_frames"], seed=meta["seeds"]["ids"], vocab_size=llm["vocab_size"])
+    sdt = ho.to_torch(sd_head)
+    eng = VisionEngine(cfg, max_tiles=8).load_state_dict(sd_vis)
+    emb = eng.extract_feature(torch.from_numpy(pv).to(torch.bfloat16).cuda())
+    motion = ho.motion_embeds(ho.fake_slowfast(torch.from_numpy(pv), 1), sdt).to(torch.bfloat16).cuda()
+    tok = sdt["language_model.model.tok_embeddings.weight"].to(torch.bfloat16).cuda()
+    x = llm_glue.splice_tokens(torch.from_numpy(ids).cuda(), tok, emb, motion, synth.IMG_CONTEXT_ID)
+    lm = L.LanguageEngine(llm, max_tokens=ids.shape[1]).load_state_dict(sd_head)
+    hid, arg, logits = lm.stage2_tail(x, n_answer=48)
+    score, pre = llm_glue.MlpScoreHead(sd_head, "cuda")(hid)
+    torch.cuda.synchronize()
+    d = abs(float(score[0]) - float(g["score1"][0]))
+    e_hid = vo.error_metrics(hid.cpu().numpy(), g["hidden_m4"])
+    ref_logits = g["logits_tail"]
+    top2 = np.sort(ref_logits, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 1e-2 * np.abs(ref_logits).max()
+    same = arg.cpu().numpy() == g["logit_tail"]
+    e_log = vo.error_metrics(logits.cpu().numpy(), ref_logits)
+    print(f"all on the GPU: score1 {float(score[0]):.4f} vs reference {float(g['score1'][0]):.4f} |d| {d:.2e} (tol 0.02); "
+          f"hidden[-4] e_max/e_l2 {e_hid}; logits {e_log}; argmax equal {int(same.sum())}/48 ({int(decided.sum())} decided)")
+    assert d <= 0.02
+    assert same[decided].all()
+
+
+def test_prefill_rejects_bad_calls(golden_dir):
+    meta, sd_head, _ = _head_case(golden_dir)
+    llm = meta["llm"]
+    eng = L.LanguageEngine(llm, max_tokens=64)
+    x = torch.zeros((1, 8, llm["hidden_size"]), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        eng.prefill(x)                       # weights not loaded
+    eng.load_state_dict(sd_head)
+    with pytest.raises(ValueError):
+        eng.prefill(torch.zeros((1, 8, 128), dtype=torch.bfloat16, device="cuda"))   # wrong width
+    with pytest.raises(ValueError):
+        eng.prefill(torch.zeros((1, 65, llm["hidden_size"]), dtype=torch.bfloat16, device="cuda"))   # beyond max_tokens
+    with pytest.raises(ValueError):
+        eng.hidden_rows([0])                 # no prefill yet
+    eng.prefill(x)
+    with pytest.raises(ValueError):
+        eng.hidden_rows([8])                 # outside the last prefill
+    with pytest.raises(ValueError):
+        eng.set_weight("model.layers.0.attention.wq.weight", torch.zeros(4))
