@@ -121,11 +121,19 @@ __device__ __forceinline__ int col_k(const AttnLayout& L, int h) {
 // tiles cover (the sequence without the class-token side row).
 template <int CHUNK, int TILES, int BKV>
 __device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, int H, int S, int s_rows, bool side_mode,
-                                            int n_blocks, bool causal) {
+                                            int n_blocks, bool causal, int n_items_total) {
     Item m;
-    const int fh = i / n_chunks;
-    const int raw = i - fh * n_chunks;
-    const int chunk = (raw + fh / rot_div) % n_chunks;
+    int fh, chunk;
+    if (causal) {   // rank i: all (frame, head) of the last chunk first, then the chunk before it, ...
+        const int FH = n_items_total / n_chunks;
+        const int c = i / FH;
+        fh = i - c * FH;
+        chunk = n_chunks - 1 - c;
+    } else {
+        fh = i / n_chunks;
+        const int raw = i - fh * n_chunks;
+        chunk = (raw + fh / rot_div) % n_chunks;
+    }
     m.frame = fh / H;
     m.head = fh - m.frame * H;
     m.q0 = chunk * CHUNK;
@@ -136,6 +144,17 @@ __device__ __forceinline__ Item decode_item(int i, int n_chunks, int rot_div, in
     // causal: keys up to the item's last query row only (blocks past a tile's own diagonal are masked, not skipped)
     m.n_b = causal ? min(n_blocks, (min(m.q0 + m.n_t * BQ, S) + BKV - 1) / BKV) : n_blocks;
     return m;
+}
+
+// Work list. Bidirectional: CTA b takes items b, b + grid, ... (items of one (frame, head) adjacent: their CTAs share K/V
+// in L2). Causal: items are ranked heaviest first (a chunk's cost grows with its position in the sequence) and dealt out
+// in a snake -- pass 0 to CTAs 0..grid-1, pass 1 to grid-1..0, ... -- so every CTA's total is close to the average instead
+// of up to twice it. Returns the item id of this CTA's it-th item, or -1 past its last one.
+template <bool kCausal>
+__device__ __forceinline__ int item_at(int it, int n_items) {
+    const int grid = static_cast<int>(gridDim.x), b = static_cast<int>(blockIdx.x);
+    const int i = it * grid + ((kCausal && (it & 1)) ? grid - 1 - b : b);
+    return i < n_items ? i : -1;
 }
 
 template <uint32_t N>
@@ -264,10 +283,9 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         reg_dec<G::REGS_SERVICE>();
         if (warp == WARP_PRODUCER) {
             // ------------------------------------------------------------ TMA producer
-            int it = 0;
             uint32_t kst = 0, kph = 0;  // K/V ring position of the next block to load
-            for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++it) {
-                const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
+            for (int it = 0, i; (i = item_at<kCausal>(it, n_items)) >= 0; ++it) {
+                const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal, n_items);
                 const int qb = it % QBUFS;
                 auto load_k = [&](int j) {
                     const int r = m.row_base + j * BKV;
@@ -336,16 +354,15 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             const uint64_t v_desc0 = umma_desc_sw128(smem_u32(smem + OFF_V), KV_ATOM, 1024);
             constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (= V) is MN-major, N = HD
-            const int my_items = (n_items > static_cast<int>(blockIdx.x))
-                                     ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
-                                     : 0;
+            int my_items = 0;
+            while (item_at<kCausal>(my_items, n_items) >= 0) ++my_items;
             const bool uniform = (s_rows % CHUNK) == 0 && !causal;  // every item: all tiles live, all key blocks
             // (live tiles, key blocks) of this CTA's it-th item
             auto geom_of = [&](int it, int& nt, int& nb) {
                 if (it >= my_items) { nt = 0; nb = n_blocks; return; }
                 if (uniform) { nt = TILES; nb = n_blocks; return; }
-                const Item m = decode_item<CHUNK, TILES, BKV>(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x),
-                                                              n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
+                const Item m = decode_item<CHUNK, TILES, BKV>(item_at<kCausal>(it, n_items), n_chunks, rot_div, H, S, s_rows,
+                                                              smode, n_blocks, causal, n_items);
                 nt = m.n_t;
                 nb = m.n_b;
             };
@@ -455,8 +472,8 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             float* qs = q_side + w * HD;
             float* ps = p_side + w * KPW;
             uint32_t kst = 0, kph = 0;
-            for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
-                const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
+            for (int it = 0, i; (i = item_at<kCausal>(it, n_items)) >= 0; ++it) {
+                const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal, n_items);
                 float m_run = -INFINITY, l_lane = 0.f, o_acc[DPL];
 #pragma unroll
                 for (int e = 0; e < DPL; ++e) o_acc[e] = 0.f;
@@ -598,8 +615,8 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
             while (sb >= static_cast<uint32_t>(NSB)) { sb -= NSB; sph ^= 1; }
         };
         advance_sb(t);  // tile t's first step is step t of the sequence (when all tiles are live; see below)
-        for (int i = blockIdx.x; i < n_items; i += gridDim.x, ++it) {
-            const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal);
+        for (int i; (i = item_at<kCausal>(it, n_items)) >= 0; ++it) {
+            const Item m = decode_item<CHUNK, TILES, BKV>(i, n_chunks, rot_div, H, S, s_rows, smode, n_blocks, causal, n_items);
             const int qb = it % QBUFS;
             const uint32_t qph = (it / QBUFS) & 1;
             // Step index of (block j, tile t) inside this item is j * n_t + t: sb/sph were positioned for tile t with all

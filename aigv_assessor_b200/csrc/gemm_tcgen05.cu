@@ -60,7 +60,7 @@ struct Cfg {
 // LN fusion: the A operand was the un-normalised activation x (bf16) and W carries gamma, so
 //   LN(x) W^T = rstd * (x W'^T - mean * wsum) + (b + W beta),   wsum[n] = sum_k W'[n,k]
 // with the row's mean / rstd taken from the (sum, sum of squares) the producing GEMM accumulated.
-template <bool kGelu>
+template <int kAct>   // 0: none, 1: erf GELU, 2: SwiGLU on (gate, up) column pairs (applied by the caller: halves the width)
 __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep, float mean, float rstd) {
     if (ep.ln_stats) {
         // x = rstd * (acc - mean * wsum) + bias as two FMAs per element: fma(rstd, acc, fma(-mean*rstd, wsum, bias))
@@ -82,7 +82,7 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
             x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
         }
     }
-    if (kGelu) {
+    if (kAct == 1) {
 #pragma unroll
 #ifdef AIGV_GELU_AS7126  // the older Abramowitz-Stegun 7.1.26 form (18 issue slots per pair; fc1 2.4% slower)
         for (int j = 0; j < 32; j += 2) gelu_erf2(x[j], x[j + 1]);
@@ -99,7 +99,7 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
     }
 }
 
-template <bool kGelu, bool kOutF32, int kEpiWarps, int kResid>
+template <int kAct, bool kOutF32, int kEpiWarps, int kResid>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<kEpiWarps, kResid>::THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
@@ -294,7 +294,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-                if (colb + c < N) epilogue_math<kGelu>(x, colb + c, ep, mean, rstd);
+                if (colb + c < N) epilogue_math<kAct>(x, colb + c, ep, mean, rstd);
             };
             auto flush = [&](const uint4 (&packed)[8], int col0) {
                 uint8_t* my_row = stg + lane * 128;
@@ -430,6 +430,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                                __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
                     flush(packed, colb + c);
                 }
+            } else if (kAct == 2) {
+                // SwiGLU (modeling_internlm2.py:275-278): W interleaves w1 / w3 rows, so accumulator columns (2i, 2i+1) are
+                // (gate, up) of output column i: out = silu(gate) * up, half as wide as the accumulator. 128 accumulator
+                // columns fill one 64-column bf16 staging tile of the [M, N/2] output.
+                static_assert(kAct != 2 || SLICE_COLS % 128 == 0, "SwiGLU epilogue needs 128-column slices");
+#pragma unroll 1
+                for (int c = 0; c < SLICE_COLS; c += 128) {
+                    uint4 packed[8];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        float x[32];
+                        load32(c + 32 * h, x);
+                        float y[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float g = x[2 * j];
+                            y[j] = __fdividef(g, 1.0f + exp2f(-1.4426950408889634f * g)) * x[2 * j + 1];
+                        }
+                        packed[2 * h] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                   pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+                        packed[2 * h + 1] = make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]),
+                                                       pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+                    }
+                    flush(packed, (colb + c) >> 1);
+                }
             } else {
 #pragma unroll 1
                 for (int c = 0; c < SLICE_COLS; c += 64) {  // 64-column bf16 staging tiles (128 B rows)
@@ -461,11 +486,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
-template <bool kGelu, bool kOutF32, int kEpiWarps, int kResid>
+template <int kAct, bool kOutF32, int kEpiWarps, int kResid>
 cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmX,
                            int M, int N, int K, const GemmEpilogue& ep, int num_sms, cudaStream_t stream) {
     using C = Cfg<kEpiWarps, kResid>;
-    auto kern = gemm_bf16_tn_kernel<kGelu, kOutF32, kEpiWarps, kResid>;
+    auto kern = gemm_bf16_tn_kernel<kAct, kOutF32, kEpiWarps, kResid>;
     static unsigned long long optin_mask = 0;  // per device (kernels.h)
     cudaError_t e = ensure_smem_optin(reinterpret_cast<const void*>(kern), C::SMEM_BYTES, optin_mask);
     if (e != cudaSuccess) return e;
@@ -493,22 +518,26 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
         // x_new = x_old + colscale*(acc+bias) in the SM; needs the bf16 copy map and 64-column-aligned N
         if (!ep.out_f32 || ep.gelu || ep.accumulate || !tmX || (N % 64) != 0) return cudaErrorInvalidValue;
         // long K: the mainloop hides a serial single-buffer epilogue and keeps all 6 stages; short K: pipelined, 4 stages
-        if (K >= 2048) return launch_variant<false, true, 8, 2>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
+        if (K >= 2048) return launch_variant<0, true, 8, 2>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
         // short K (proj): the epilogue is the critical path. The serial form is too slow for it even on 16 warps with
         // two chunks each (4.6 vs 4.2 ms/step, same-box A/B), so x_old is double-buffered at the price of 4 stages.
-        return launch_variant<false, true, 8, 1>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
+        return launch_variant<0, true, 8, 1>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
     }
     // The GELU epilogue is instruction-issue heavy: 16 epilogue warps and 5 stages; everything else 8 warps and 6 stages
     // (measured: the fp32 reduce-add epilogue of proj does not gain from more warps: 948 vs 1016 TFLOP/s).
+    if (ep.swiglu) {  // tmC describes the [M, N/2] bf16 output
+        if (ep.out_f32 || ep.gelu || ep.accumulate || ep.colscale || (N % 128) != 0) return cudaErrorInvalidValue;
+        return launch_variant<2, false, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    }
     if (ep.gelu) {
 #ifndef AIGV_GELU_WARPS
 #define AIGV_GELU_WARPS 16
 #endif
-        return ep.out_f32 ? launch_variant<true, true, AIGV_GELU_WARPS, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream)
-                          : launch_variant<true, false, AIGV_GELU_WARPS, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+        return ep.out_f32 ? launch_variant<1, true, AIGV_GELU_WARPS, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream)
+                          : launch_variant<1, false, AIGV_GELU_WARPS, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
     }
-    if (ep.out_f32) return launch_variant<false, true, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
-    return launch_variant<false, false, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    if (ep.out_f32) return launch_variant<0, true, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    return launch_variant<0, false, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
 }
 
 }  // namespace aigv

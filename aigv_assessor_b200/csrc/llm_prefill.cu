@@ -18,6 +18,7 @@
 // unpadded prompts), the KV cache / decode steps, dynamic-NTK rescaling beyond max_position_embeddings (LLM:218-244 leaves
 // the base unchanged below it).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -208,7 +209,8 @@ struct aigv_llm_handle {
     int64_t launches = 0;
     // activation maps, rebuilt when the token count changes
     int maps_m = -1;
-    CUtensorMap a_xb, a_attn, a_hm, q_map, kv_map, c_x, c_xb, c_qkv, c_h13;
+    CUtensorMap a_xb, a_attn, a_hm, q_map, kv_map, c_x, c_xb, c_qkv, c_h13, c_hm;
+    bool fused_swiglu = true;   // AIGV_LLM_UNFUSED_SWIGLU=1: w1|w3 GEMM -> h13, then the standalone SwiGLU kernel (A/B runs)
 };
 
 namespace {
@@ -253,6 +255,7 @@ int build_maps(aigv_llm_handle* h, int M) {
     r |= make_tmap_2d(&h->c_xb, h->xb, 0, M, h->H, h->H, cr, cb);
     r |= make_tmap_2d(&h->c_qkv, h->qkv, 0, M, h->QW, h->QW, cr, cb);
     r |= make_tmap_2d(&h->c_h13, h->h13, 0, M, 2 * h->I, 2 * h->I, cr, cb);
+    r |= make_tmap_2d(&h->c_hm, h->hm, 0, M, h->I, h->I, cr, cb);
     if (r) return -1;
     h->maps_m = M;
     return 0;
@@ -299,6 +302,10 @@ int aigv_llm_create(const aigv_llm_cfg* cfg, aigv_llm_handle** out) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     h->num_sms = sms > 0 ? sms : 148;
     h->layers.resize(h->L);
+    {
+        const char* e = getenv("AIGV_LLM_UNFUSED_SWIGLU");
+        h->fused_swiglu = !(e && e[0] == '1') && (h->I % 64) == 0;
+    }
     const size_t M = h->Mx;
     bool ok = lalloc(h, &h->x, M * h->H) && lalloc(h, &h->xb, M * h->H) && lalloc(h, &h->qkv, M * h->QW) &&
               lalloc(h, &h->attn, M * h->H) && lalloc(h, &h->h13, M * 2 * h->I) && lalloc(h, &h->hm, M * h->I) &&
@@ -471,8 +478,12 @@ int aigv_llm_prefill(aigv_llm_handle* h, const void* inputs_embeds_bf16, int B, 
         }
         LLM_LAUNCH(launch_attention2(h->q_map, h->kv_map, h->qkv, h->attn, B, N, h->nh, h->hd, scale, h->num_sms, st, &lay), "causal attention");
         LLM_LAUNCH(launch_gemm(h->a_attn, w.tm_wo, h->c_x, M, H, H, prod, h->num_sms, st, &h->c_xb), "wo");
-        LLM_LAUNCH(launch_gemm(h->a_xb, w.tm_w13, h->c_h13, M, 2 * h->I, H, cons, h->num_sms, st), "w1|w3");
-        {
+        if (h->fused_swiglu) {   // silu(gate) * up in the epilogue: the [M, 2I] intermediate never reaches HBM
+            GemmEpilogue sw = cons;
+            sw.swiglu = 1;
+            LLM_LAUNCH(launch_gemm(h->a_xb, w.tm_w13, h->c_hm, M, 2 * h->I, H, sw, h->num_sms, st), "w1|w3 + swiglu");
+        } else {
+            LLM_LAUNCH(launch_gemm(h->a_xb, w.tm_w13, h->c_h13, M, 2 * h->I, H, cons, h->num_sms, st), "w1|w3");
             const size_t n8 = (size_t)M * h->I / 8;
             LLM_LAUNCH((llm_silu_mul_kernel<<<(unsigned)std::min<size_t>((n8 + 255) / 256, 148 * 16), 256, 0, st>>>(h->h13, h->hm, n8), cudaGetLastError()), "swiglu");
         }
