@@ -456,6 +456,42 @@ def run_native(args, rank, local_rank, world, out):
         except Exception as e:  # a side measurement must never take the bench line down
             extra["config5_internvit_6b"] = {"unavailable": repr(e)[:300]}
 
+    # ---- next-1: InternLM2-7B prefill of one 8-frame clip prompt (2108 tokens), one replica per GPU ----------
+    if not args.no_extra and not args.no_llm:
+        try:
+            import tools_bench_llm as tbl
+            torch.cuda.empty_cache()
+            n_tok = 1 + 8 * 258 + 3 + 40      # <s>, 8 x (<img> 256 x <IMG_CONTEXT> </img>), the motion slot, 40 text tokens
+            c7, lm = tbl.build("7b", n_tok)
+            x7 = (torch.randn((1, n_tok, c7["hidden_size"]), device=dev) * 0.5).to(torch.bfloat16)
+            tail = list(range(n_tok - 49, n_tok - 1))
+
+            def clip_tail():
+                lm.prefill(x7)
+                lm.hidden_rows([n_tok - 4])
+                return lm.logits_rows(tail)
+            for _ in range(2):
+                lg = clip_tail()
+            ms7 = timed(clip_tail, 5)
+            fl7 = tbl.flops_per_prompt(c7, n_tok)
+            extra["next1_llm_prefill_7b"] = {
+                "prompts_per_s": world / ms7 * 1e3, "ms_per_prompt": ms7, "tokens": n_tok, "tflops_per_gpu": fl7 / ms7 / 1e9,
+                "frac_of_sustained_peak": fl7 / ms7 / 1e9 / measured_peaks()["sustained"], "tflop_per_prompt": fl7 / 1e12,
+                "finite": bool(torch.isfinite(lg).all()), "launches_per_prompt": 1 + 6 * c7["num_hidden_layers"] + 3,
+                "note": "InternLM2-7B decoder stack (32L, 4096, 32/8 heads of 128, I=14336) on the spliced prompt of one 8-frame "
+                        "clip: RMSNorm-fused wqkv, rotary, causal GQA tcgen05 attention, wo + residual, w1|w3 + SwiGLU epilogue, w2 + "
+                        "residual; final norm + output head on row -4 and the 48 answer rows only; random-init weights on the device"}
+            if world == 1 and not args.no_ref_gpu:
+                try:
+                    extra["next1_llm_prefill_7b"]["reference_gpu_stack"] = tbl.reference_gpu_stack(c7, 1, n_tok)
+                except Exception as e:
+                    extra["next1_llm_prefill_7b"]["reference_gpu_stack"] = {"unavailable": repr(e)[:200]}
+            lm.close()
+            del lm, x7
+            torch.cuda.empty_cache()
+        except Exception as e:  # a side measurement must never take the bench line down
+            extra["next1_llm_prefill_7b"] = {"unavailable": repr(e)[:300]}
+
     ms = max_over_ranks(ms_local)
     ms_e2e = max_over_ranks(ms_e2e_local)
     rank_ms = [ms_local / args.steps]
@@ -578,6 +614,7 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-GPU-stack comparator (cuBLASLt / FA2)")
     ap.add_argument("--no-extra", action="store_true", help="skip the config 3 / 4 / 5 side measurements")
     ap.add_argument("--no-6b", action="store_true", help="skip the InternViT-6B (config 5) side measurement")
+    ap.add_argument("--no-llm", action="store_true", help="skip the InternLM2-7B prefill (next-1) side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
