@@ -83,29 +83,37 @@ __global__ void llm_rope_table_kernel(float2* __restrict__ tab, int N, int half,
 
 // In place on the wqkv output [M, pitch]: every q head and the k head of each kv group (slots 0..G of the G + 2 per
 // group) get out[j] = x[j] cos_j - x[j + d/2] sin_j, out[j + d/2] = x[j + d/2] cos_j + x[j] sin_j  (LLM:247-260), computed
-// in fp32 from the bf16 values and rounded once. One thread per (token, rotary head, pair of j).
+// in fp32 from the bf16 values and rounded once. One thread per (token, rotary head, 8 consecutive j): 16-byte accesses.
 __global__ void __launch_bounds__(256)
 llm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float2* __restrict__ tab, int M, int N, int pitch, int n_kv, int G,
                 int hd) {
-    const int half = hd >> 1, pairs = half >> 1;     // two j per thread (one 32-bit word from each half)
-    const int per_row = n_kv * (G + 1) * pairs;
+    const int half = hd >> 1, octs = half >> 3;
+    const int per_row = n_kv * (G + 1) * octs;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(M) * per_row) return;
     const int row = static_cast<int>(idx / per_row);
     int rem = static_cast<int>(idx - static_cast<long long>(row) * per_row);
-    const int jp = rem % pairs;
-    rem /= pairs;
+    const int jo = rem % octs;
+    rem /= octs;
     const int slot = rem % (G + 1), g = rem / (G + 1);
     const int pos = row % N;
     __nv_bfloat16* base = qkv + static_cast<size_t>(row) * pitch + (g * (G + 2) + slot) * hd;
-    uint32_t* lo = reinterpret_cast<uint32_t*>(base + 2 * jp);
-    uint32_t* hi = reinterpret_cast<uint32_t*>(base + half + 2 * jp);
-    const uint32_t a = *lo, b = *hi;
-    const float2 c0 = tab[static_cast<size_t>(pos) * half + 2 * jp], c1 = tab[static_cast<size_t>(pos) * half + 2 * jp + 1];
-    const float a0 = __uint_as_float(a << 16), a1 = __uint_as_float(a & 0xffff0000u);
-    const float b0 = __uint_as_float(b << 16), b1 = __uint_as_float(b & 0xffff0000u);
-    *lo = pack_bf16x2(a0 * c0.x - b0 * c0.y, a1 * c1.x - b1 * c1.y);
-    *hi = pack_bf16x2(b0 * c0.x + a0 * c0.y, b1 * c1.x + a1 * c1.y);
+    uint4* lo = reinterpret_cast<uint4*>(base + 8 * jo);
+    uint4* hi = reinterpret_cast<uint4*>(base + half + 8 * jo);
+    const uint4 a = *lo, b = *hi;
+    const float4* cs = reinterpret_cast<const float4*>(tab + static_cast<size_t>(pos) * half + 8 * jo);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ow[4], pw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float4 c = __ldg(cs + e);   // (cos, sin) of j = 8 jo + 2 e and of the next j
+        const float a0 = __uint_as_float(aw[e] << 16), a1 = __uint_as_float(aw[e] & 0xffff0000u);
+        const float b0 = __uint_as_float(bw[e] << 16), b1 = __uint_as_float(bw[e] & 0xffff0000u);
+        ow[e] = pack_bf16x2(a0 * c.x - b0 * c.y, a1 * c.z - b1 * c.w);
+        pw[e] = pack_bf16x2(b0 * c.x + a0 * c.y, b1 * c.z + a1 * c.w);
+    }
+    *lo = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    *hi = make_uint4(pw[0], pw[1], pw[2], pw[3]);
 }
 
 // SwiGLU on the interleaved w1 / w3 output: out[m, i] = silu(h[m, 2i]) * h[m, 2i + 1]  (LLM:275-278)
@@ -473,7 +481,7 @@ int aigv_llm_prefill(aigv_llm_handle* h, const void* inputs_embeds_bf16, int B, 
         prod.out_f32 = 1; prod.fused_residual = 1; prod.resid_in = h->x; prod.stats_out = h->stats;
         LLM_LAUNCH(launch_gemm(h->a_xb, w.tm_wqkv, h->c_qkv, M, h->QW, H, cons, h->num_sms, st), "wqkv");
         {
-            const long long n = (long long)M * h->nkv * (h->G + 1) * (half / 2);
+            const long long n = (long long)M * h->nkv * (h->G + 1) * (half / 8);
             LLM_LAUNCH((llm_rope_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->qkv, h->rope, M, N, h->QW, h->nkv, h->G, h->hd), cudaGetLastError()), "rope");
         }
         LLM_LAUNCH(launch_attention2(h->q_map, h->kv_map, h->qkv, h->attn, B, N, h->nh, h->hd, scale, h->num_sms, st, &lay), "causal attention");
@@ -559,13 +567,13 @@ int aigv_attention_gqa(const void* qkv_bf16, void* out_bf16, int B, int N, int h
 }
 
 int aigv_rope(void* qkv_bf16, int B, int N, int heads, int kv_heads, int head_dim, float theta, void* stream) {
-    if (!qkv_bf16 || B <= 0 || N <= 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads || head_dim % 4) return AIGV_ERR_INVALID;
+    if (!qkv_bf16 || B <= 0 || N <= 0 || heads <= 0 || kv_heads <= 0 || heads % kv_heads || head_dim % 16) return AIGV_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int G = heads / kv_heads, half = head_dim / 2, M = B * N, QW = (heads + 2 * kv_heads) * head_dim;
     float2* tab = nullptr;
     if (cudaMalloc(&tab, (size_t)N * half * sizeof(float2)) != cudaSuccess) return AIGV_ERR_CUDA;
     llm_rope_table_kernel<<<(N * half + 255) / 256, 256, 0, st>>>(tab, N, half, theta, (float)head_dim);
-    const long long n = (long long)M * kv_heads * (G + 1) * (half / 2);
+    const long long n = (long long)M * kv_heads * (G + 1) * (half / 8);
     llm_rope_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<__nv_bfloat16*>(qkv_bf16), tab, M, N, QW, kv_heads, G, head_dim);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(tab);

@@ -117,7 +117,8 @@ def reference_gpu_stack(c, B, N, reps=3):
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "7b"
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 2108
-    Bs = [int(v) for v in sys.argv[3:]] or [1, 2, 4]
+    noref = "noref" in sys.argv
+    Bs = [int(v) for v in sys.argv[3:] if v != "noref"] or [1, 2, 4]
     t0 = time.time()
     c, eng = build(name, max(Bs) * N)
     torch.cuda.synchronize()
@@ -141,7 +142,7 @@ def main():
         ms = e0.elapsed_time(e1) / reps
         fl = flops_per_prompt(c, N) * B
         ref = None
-        if B == Bs[0]:
+        if B == Bs[0] and not noref:
             try:
                 ref = reference_gpu_stack(c, B, N)
             except Exception as e:  # comparator only
