@@ -175,3 +175,35 @@ def test_prefill_rejects_bad_calls(golden_dir):
         eng.hidden_rows([8])                 # outside the last prefill
     with pytest.raises(ValueError):
         eng.set_weight("model.layers.0.attention.wq.weight", torch.zeros(4))
+
+
+def test_clip_scorer_reproduces_the_reference_forward(golden_dir):
+    """scoring.ClipScorer = the eval-time forward (eval2 :306-488) with every module of the reference replaced by this
+    library (motion_mlp included; only the SlowFast stand-in's 2304-vector comes from the host): score1 and the answer-span
+    argmax against the golden the unmodified reference produced, for both vision towers of the goldens."""
+    from aigv_assessor_b200.config import VisionPathConfig
+    from aigv_assessor_b200.scoring import ClipScorer
+    for name in ("tiny", "vit300m"):
+        meta, sd_head, g = _head_case(golden_dir, name)
+        cfg = VisionPathConfig(**meta["vis_cfg"])
+        sd = dict(synth.make_weights(cfg, seed=meta["seeds"]["vis"]))
+        sd.update(sd_head)
+        pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["seeds"]["x"])
+        ids = synth.make_clip_prompt(meta["n_frames"], seed=meta["seeds"]["ids"], vocab_size=meta["llm"]["vocab_size"])
+        scorer = ClipScorer(sd, cfg, meta["llm"], synth.IMG_CONTEXT_ID, max_tiles=8, max_tokens=ids.shape[1])
+        feat = ho.fake_slowfast(torch.from_numpy(pv), 1)           # what eval2 :343 hands to motion_mlp
+        out = scorer(torch.from_numpy(pv).to(torch.bfloat16).cuda(), torch.from_numpy(ids).cuda(), feat.cuda())
+        torch.cuda.synchronize()
+        d = abs(float(out["score1"][0]) - float(g["score1"][0]))
+        ref_logits = g["logits_tail"]
+        top2 = np.sort(ref_logits, axis=1)[:, -2:]
+        decided = (top2[:, 1] - top2[:, 0]) > 1e-2 * np.abs(ref_logits).max()
+        same = out["logit"].cpu().numpy() == g["logit_tail"]
+        ref_mot = ho.motion_embeds(feat, ho.to_torch(sd_head))
+        e_mot = float((scorer.motion(feat.cuda()).float().cpu() - ref_mot).abs().max() / ref_mot.abs().max())
+        print(f"ClipScorer[{name}]: score1 {float(out['score1'][0]):.4f} vs reference {float(g['score1'][0]):.4f} |d| {d:.2e}; "
+              f"motion token e_max {e_mot:.2e}; argmax equal {int(same.sum())}/48 ({int(decided.sum())} decided)")
+        assert e_mot < 2e-2
+        assert d <= 0.02
+        assert same[decided].all()
+        del scorer
