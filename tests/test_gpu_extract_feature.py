@@ -272,3 +272,21 @@ def test_lora_wrapped_tower_and_safetensors_ingest(tmp_path):
     checkpoint.write_safetensors(path, peft)
     y_ckpt = VisionEngine(cfg, max_tiles=2).load_checkpoint(path).extract_feature(pv)
     assert torch.equal(y_ckpt, y_peft)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_engines_on_two_devices_of_one_process():
+    """Function attributes (the > 48 KB shared-memory opt-in) and the SM count are per device: a second engine on another
+    GPU of the same process must work and give the same bits."""
+    cfg = tiny()
+    sd = synth.make_weights(cfg, seed=7)
+    pv = torch.from_numpy(synth.make_pixel_values(3, cfg, seed=8)).to(torch.bfloat16)
+    outs = []
+    for d in (0, 1):
+        eng = VisionEngine(cfg, max_tiles=4, device=f"cuda:{d}").load_state_dict(sd)
+        outs.append(eng.extract_feature(pv.to(f"cuda:{d}")).float().cpu())
+        with pytest.raises(ValueError):
+            eng.extract_feature(pv.to(f"cuda:{1 - d}"))      # tensors on another device are refused, not launched
+    torch.cuda.synchronize(0)
+    torch.cuda.synchronize(1)
+    assert torch.equal(outs[0], outs[1])
