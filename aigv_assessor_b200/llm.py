@@ -89,7 +89,13 @@ class LanguageEngine:
         self._check(st, f"aigv_llm_set_weight({name})")
 
     def load_state_dict(self, sd: Mapping[str, object], prefix: str = "language_model.") -> "LanguageEngine":
-        """Reference state-dict names (modeling_internlm2.py parameter names under ``language_model.``)."""
+        """Reference state-dict names (modeling_internlm2.py parameter names under ``language_model.``). LoRA pairs of a
+        peft-wrapped LLM ('...base_layer.weight' + 'lora_A/lora_B.default.weight'; the stage-2 checkpoints wrap wqkv / wo /
+        w1 / w2 / w3, eval2 :285-305) are folded first: W + 2 B A as tools/merge_lora.py:18-25 does."""
+        if any(".lora_A." in k for k in sd):
+            from .engine import merge_lora_names
+            sd = merge_lora_names({k: (torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v)
+                                   for k, v in sd.items() if k.startswith(prefix) or "language_model" in k})
         for i in range(self.layers):
             for n in _NAMES:
                 self.set_weight(f"model.layers.{i}.{n}", sd[f"{prefix}model.layers.{i}.{n}"])

@@ -188,3 +188,47 @@ def test_safetensors_roundtrip_and_selective_read(tmp_path):
     empty.mkdir()
     with pytest.raises(FileNotFoundError):
         checkpoint.load_checkpoint_dir(str(empty))
+
+
+def test_frame_sampling_matches_the_reference_get_index(golden_dir):
+    """sampling.frame_indices against 896 index vectors produced by the reference's own get_index (stage1_eval.py:429-441)."""
+    import json
+    from aigv_assessor_b200 import sampling
+    with open(os.path.join(golden_dir, "golden_sampling.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) > 500
+    for c in cases:
+        got = sampling.frame_indices(c["max_frame"] + 1, c["fps"], c["num_segments"], bound=c["bound"])
+        assert got.tolist() == c["indices"], c
+    frames = torch.arange(10 * 2 * 2 * 3, dtype=torch.uint8).reshape(10, 2, 2, 3)
+    pick = sampling.gather_frames(frames, [0, 4, 9])
+    assert torch.equal(pick, frames[[0, 4, 9]])
+    with pytest.raises(ValueError):
+        sampling.gather_frames(frames, [10])
+    with pytest.raises(ValueError):
+        sampling.frame_indices(0, 30.0)
+
+
+def test_language_engine_fails_loudly_without_cuda_and_merges_lora_names():
+    from aigv_assessor_b200 import _lib, llm
+    from aigv_assessor_b200.engine import merge_lora_names
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.AigvError):
+            llm.LanguageEngine(dict(hidden_size=256, num_hidden_layers=1, num_attention_heads=2, num_key_value_heads=1,
+                                    intermediate_size=256, vocab_size=64, rms_norm_eps=1e-5))
+    # peft-style names of a LoRA-wrapped InternLM2 linear fold to the plain reference name: W + 2 B A
+    g = torch.Generator().manual_seed(0)
+    W, A, B = torch.randn(8, 6, generator=g), torch.randn(2, 6, generator=g), torch.randn(8, 2, generator=g)
+    sd = {"language_model.base_model.model.model.layers.0.attention.wqkv.base_layer.weight": W,
+          "language_model.base_model.model.model.layers.0.attention.wqkv.lora_A.default.weight": A,
+          "language_model.base_model.model.model.layers.0.attention.wqkv.lora_B.default.weight": B}
+    out = merge_lora_names(sd)
+    assert list(out) == ["language_model.model.layers.0.attention.wqkv.weight"]
+    assert torch.allclose(out["language_model.model.layers.0.attention.wqkv.weight"], W + 2.0 * B @ A)
+
+
+def test_clip_prompt_has_the_call_shape_of_the_video_prompt():
+    from aigv_assessor_b200 import synth
+    ids = synth.make_clip_prompt(8)
+    assert ids.shape == (1, 1 + 8 * 258 + 3 + 40)
+    assert int((ids == synth.IMG_CONTEXT_ID).sum()) == 8 * 256 + 1   # 2048 visual slots + the motion slot (eval2 :351-378)
