@@ -129,7 +129,7 @@ struct LayerW {
 struct ActMaps {
     int n = -1;
     CUtensorMap patches, xn, attn, h, ps, m1, qkv_q, qkv_kv;   // TMA loads (GEMM A operands, attention)
-    CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out, xb_out;      // TMA stores / reduce-adds (GEMM outputs)
+    CUtensorMap pe_out, x_out, qkv_out, h_out, m1_out, xb_out, dlt_out;      // TMA stores / reduce-adds (GEMM outputs)
 };
 
 enum KClass { K_IM2COL = 0, K_GEMM_PATCH, K_ASSEMBLE, K_NORM, K_GEMM_QKV, K_QKNORM, K_ATTENTION, K_GEMM_PROJ,
@@ -171,12 +171,14 @@ struct aigv_handle {
     int max_tiles = 0;
     size_t ws_bytes = 0;
     float *x = nullptr, *pe = nullptr;
+    __nv_bfloat16* dlt = nullptr;   // "delta" scheme: proj's residual update, pending until fc2 folds it into the fp32 master
     __nv_bfloat16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *patches = nullptr, *ps = nullptr,
                   *m1 = nullptr;
     ActMaps maps;
     // LayerNorm-fused schedule (default; AIGV_FUSED_LN=0 selects the standalone norm kernels): the proj/fc2 epilogues
     // produce the residual stream, its bf16 copy (in xn) and per-token statistics; qkv/fc1 apply the norm in theirs.
     bool fused_ln = true;
+    bool delta_proj = false;   // proj leaves the fp32 master alone (gemm_tcgen05.cu kResid == 3); AIGV_DELTA_PROJ=0 disables
     int stat_parts = 0;          // D / gemm_stats_slice_cols(), rounded up
     float2* stats = nullptr;     // [stat_parts][max_tiles * S]
     // front end
@@ -226,6 +228,7 @@ size_t workspace_bytes_for(const aigv_handle* h, int t) {
     b += M * h->D * 2;        // xn
     b += M * 3 * h->D * 2;    // qkv
     b += M * h->D * 2;        // attn
+    b += M * h->D * 2;        // dlt
     b += M * h->I * 2;        // h
     b += Mp * h->kpad * 2;    // patches
     b += Mo * h->W4 * 2;      // ps
@@ -254,6 +257,7 @@ int build_act_maps(aigv_handle* h, int n) {
     r |= make_tmap_2d(&h->maps.h_out, h->hbuf, 0, M, h->I, h->I, cr, cb);
     r |= make_tmap_2d(&h->maps.m1_out, h->m1, 0, Mo, h->C, h->C, cr, cb);
     r |= make_tmap_2d(&h->maps.xb_out, h->xn, 0, M, h->D, h->D, cr, cb);
+    r |= make_tmap_2d(&h->maps.dlt_out, h->dlt, 0, M, h->D, h->D, cr, cb);
     if (r) return -1;
     h->maps.n = n;
     return 0;
@@ -340,6 +344,9 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
     {
         const char* e = getenv("AIGV_FUSED_LN");
         h->fused_ln = !(e && e[0] == '0') && (h->D % 64 == 0);
+        // short-K proj (the epilogue-critical form) of a fused-LN tower whose fc2 is long-K (the serial form folds the update)
+        const char* e2 = getenv("AIGV_DELTA_PROJ");
+        h->delta_proj = h->fused_ln && !(e2 && e2[0] == '0') && h->D < 2048 && h->I >= 2048;
     }
 
     const size_t D = h->D, I = h->I, C = h->C;
@@ -427,6 +434,7 @@ int aigv_create(const aigv_cfg* cfg, aigv_handle** out) {
         ok &= dev_alloc(h, &h->xn, M * D, true);
         ok &= dev_alloc(h, &h->qkv, M * 3 * D, true);
         ok &= dev_alloc(h, &h->attn, M * D, true);
+        ok &= dev_alloc(h, &h->dlt, M * D, true);
         ok &= dev_alloc(h, &h->hbuf, M * I, true);
         ok &= dev_alloc(h, &h->patches, Mp * h->kpad, true);
         ok &= dev_alloc(h, &h->ps, Mo * h->W4, true);
@@ -643,8 +651,13 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
             GemmEpilogue ep;
             ep.bias = w.proj_b; ep.colscale = w.ls1;  // x += ls1 * (attn W^T + b)
             residual_producer(ep);
-            AIGV_LAUNCH(K_GEMM_PROJ, launch_gemm(h->maps.attn, w.tm_proj, h->maps.x_out, M, D, D, ep, h->num_sms, st,
-                                                 &h->maps.xb_out), "proj gemm");
+            if (h->delta_proj) {   // xb = bf16(xb + d) in place, d -> dlt; the fp32 master waits for fc2
+                ep.out_f32 = 0;
+                ep.delta_out = 1;
+                ep.resid_in = nullptr;
+            }
+            AIGV_LAUNCH(K_GEMM_PROJ, launch_gemm(h->maps.attn, w.tm_proj, h->delta_proj ? h->maps.dlt_out : h->maps.x_out, M, D, D, ep,
+                                                 h->num_sms, st, &h->maps.xb_out), "proj gemm");
         }
         // V2 norm2 -> V6 fc1+GELU -> V7 fc2 * ls2 + residual
         if (!fused)
@@ -661,6 +674,7 @@ static int forward_batch(aigv_handle* h, const __nv_bfloat16* pv, int n, __nv_bf
             GemmEpilogue ep;
             ep.bias = w.fc2_b; ep.colscale = w.ls2;  // x += ls2 * (h W^T + b)
             residual_producer(ep);
+            if (h->delta_proj) ep.delta_in = h->dlt;   // x_new = x_old + d(proj) + ls2 * (h W^T + b)
             AIGV_LAUNCH(K_GEMM_FC2, launch_gemm(h->maps.h, w.tm_fc2, h->maps.x_out, M, D, I, ep, h->num_sms, st,
                                                 &h->maps.xb_out), "fc2 gemm");
         }

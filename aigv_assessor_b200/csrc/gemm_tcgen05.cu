@@ -43,14 +43,19 @@ constexpr uint32_t TMEM_COLS = 512;
 // fetch, the fp32 x_new store and the bf16 copy and keeps 6 stages (measured: 4 instead of 6 stages costs 8% on fc2);
 // kResid == 1 (short K, proj: the epilogue is the critical path) needs
 // three staging tiles per warp (two fp32 tiles for the x_old prefetch / x_new store, one bf16 tile) and runs 4 stages.
+// kResid == 3 ("delta" producer, the 300M tower's proj): proj is HBM-bound on the fp32 residual stream (269 MB read + 269 MB
+// written per launch on top of 134 + 134 MB of bf16), so it does not touch the fp32 master at all: it reads the bf16 copy
+// xb_old, writes xb_new = bf16(xb_old + d) in place and the update d = colscale * (acc + bias) as bf16; the NEXT producer
+// (fc2, kResid == 2 with ep.delta_in) folds d into the master: x_new = x_old + d + colscale * (acc + bias). 536 instead of
+// 806 MB per proj launch; fc2 (compute-bound, long mainloop) reads 134 MB more.
 template <int kEpiWarps, int kResid>
 struct Cfg {
     static constexpr int EPI_WARPS = kEpiWarps;          // multiple of 4: warp%4 = TMEM lane quadrant
     static constexpr int SLICES = kEpiWarps / 4;         // column slices of the 256-column tile
     static constexpr int SLICE_COLS = BN / SLICES;       // 64 or 128 columns per warp
-    static constexpr int STAGES = kResid == 1 ? 4 : (kEpiWarps == 16 ? 5 : 6);
+    static constexpr int STAGES = (kResid == 1 || kResid == 3) ? 4 : (kEpiWarps == 16 ? 5 : 6);
     static constexpr int THREADS = (kEpiWarps + 2) * 32;
-    static constexpr int WARP_STG = kResid == 1 ? 3 * STG_BYTES : STG_BYTES;
+    static constexpr int WARP_STG = (kResid == 1 || kResid == 3) ? 3 * STG_BYTES : STG_BYTES;
     static constexpr int OFF_STG = STAGES * STAGE_BYTES;
     static constexpr int OFF_BAR = OFF_STG + kEpiWarps * WARP_STG;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;     // 2*STAGES + 4 pipeline barriers, 2 per epilogue warp, TMEM slot
@@ -237,16 +242,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // kResid: x_old does not depend on the MMAs: start fetching this warp's first staging tile before waiting
             auto issue_xload = [&](int c) {
                 if (lane == 0 && row0 < M && colb + c < N) {
-                    const int buf = kResid == 2 ? 0 : (c >> 5) & 1;  // the serial form has a single staging tile
+                    // kResid 2: a single staging tile; 1: fp32 tiles alternate per 32-column chunk; 3: bf16 tiles per 64 columns
+                    const int buf = kResid == 2 ? 0 : (kResid == 3 ? (c >> 6) & 1 : (c >> 5) & 1);
                     uint64_t* bar = &xload_bar[2 * warp + buf];
                     mbar_arrive_expect_tx(bar, STG_BYTES);
-                    tma_load_2d(stg + buf * STG_BYTES, &tmC, bar, colb + c, row0);
+                    tma_load_2d(stg + buf * STG_BYTES, kResid == 3 ? &tmX : &tmC, bar, colb + c, row0);
                 }
             };
             if (kResid) {
                 if (lane == 0) tma_store_wait_read<0>();  // staging tiles of the previous output tile have been read out
                 __syncwarp();
                 issue_xload(0);
+                if (kResid == 3 && SLICE_COLS > 64) issue_xload(64);   // both 64-column groups of the slice, a mainloop ahead
                 // x_old is streamed from HBM (the residual stream is 4 B x M x N, far beyond L2): pull this warp's rows of
                 // the NEXT tile into L2 now, a whole mainloop ahead of the TMA fetches that will want them (and the
                 // current tile's rows for the first tile of this CTA pair).
@@ -314,7 +321,56 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tma_store_commit();
                 }
             };
-            if (kResid == 2) {
+            if (kResid == 3) {
+                // "Delta" producer: xb_new = bf16(xb_old + d) in place, d = colscale * (acc + bias) out as bf16, row statistics
+                // of the new value; the fp32 master is brought up to date by the next producer (ep.delta_in there).
+                static_assert(kResid != 3 || SLICE_COLS == 128, "two 64-column groups per warp");
+                uint8_t* dtile = stg + 2 * STG_BYTES;
+#pragma unroll 1
+                for (int g = 0; g < SLICE_COLS / 64; ++g) {
+                    float xa[32], xc[32];
+                    load32(64 * g, xa);
+                    load32(64 * g + 32, xc);
+                    if (!(row0 < M && colb + 64 * g < N)) continue;  // warp-uniform (N is a multiple of 64)
+                    mbar_wait(&xload_bar[2 * warp + g], (xphase >> g) & 1);
+                    xphase ^= 1u << g;
+                    if (g) {   // the d tile of group 0 must have been read out by its store
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+                    }
+                    uint8_t* lrow = stg + g * STG_BYTES + lane * 128;
+                    uint8_t* drow = dtile + lane * 128;
+                    float rs = 0.f, rq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float* xx = j < 4 ? &xa[8 * j] : &xc[8 * (j - 4)];
+                        uint4* slot = reinterpret_cast<uint4*>(lrow + ((j ^ sw) << 4));
+                        const uint4 o = *slot;
+                        const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                        uint32_t yw[4], dw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float y0 = __uint_as_float(ow[e] << 16) + xx[2 * e];
+                            const float y1 = __uint_as_float(ow[e] & 0xffff0000u) + xx[2 * e + 1];
+                            rs += y0 + y1;
+                            rq += y0 * y0 + y1 * y1;
+                            yw[e] = pack_bf16x2(y0, y1);
+                            dw[e] = pack_bf16x2(xx[2 * e], xx[2 * e + 1]);
+                        }
+                        *slot = make_uint4(yw[0], yw[1], yw[2], yw[3]);
+                        *reinterpret_cast<uint4*>(drow + ((j ^ sw) << 4)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmX, stg + g * STG_BYTES, colb + 64 * g, row0);   // xb_new (in place over xb_old)
+                        tma_store_2d(&tmC, dtile, colb + 64 * g, row0);                  // d, bf16
+                        tma_store_commit();
+                    }
+                    if (ep.stats_out && row0 + lane < M)
+                        ep.stats_out[static_cast<size_t>((colb + 64 * g) / STATS_COLS) * M + row0 + lane] = make_float2(rs, rq);
+                }
+            } else if (kResid == 2) {
                 // Fused residual producer, serial form: one staging tile per warp. Per 32-column chunk: x_old (TMA) ->
                 // in-place x_new -> fp32 store -> (every second chunk) the 64-column bf16 copy through the same tile ->
                 // fetch of the next chunk. Every step waits for the previous one; the long mainloop hides it.
@@ -327,6 +383,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     float x[32];
                     load32(c, x);
                     if (!(row0 < M && colb + c < N)) continue;  // warp-uniform: nothing of this chunk is inside C
+                    if (ep.delta_in && row0 + lane < M) {
+                        // the previous ("delta") producer's update, not yet in the fp32 master: this row's 32 bf16 values
+                        const uint4* dp = reinterpret_cast<const uint4*>(ep.delta_in + static_cast<size_t>(row0 + lane) * N + colb + c);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 dv = __ldg(dp + q);
+                            const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                x[8 * q + 2 * e] += __uint_as_float(dw[e] << 16);
+                                x[8 * q + 2 * e + 1] += __uint_as_float(dw[e] & 0xffff0000u);
+                            }
+                        }
+                    }
                     mbar_wait(&xload_bar[2 * warp], xphase & 1);
                     xphase ^= 1u;
 #pragma unroll
@@ -525,7 +595,13 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     if (ep.accumulate && !ep.out_f32) return cudaErrorInvalidValue;
     if (ep.fused_residual) {
         // x_new = x_old + colscale*(acc+bias) in the SM; needs the bf16 copy map and 64-column-aligned N
-        if (!ep.out_f32 || ep.gelu || ep.accumulate || !tmX || (N % 64) != 0) return cudaErrorInvalidValue;
+        if (ep.gelu || ep.accumulate || !tmX || (N % 64) != 0) return cudaErrorInvalidValue;
+        if (ep.delta_out) {   // tmC = the bf16 update matrix d, tmX = the bf16 copy xb (read and rewritten in place)
+            if (ep.out_f32 || ep.delta_in) return cudaErrorInvalidValue;
+            return launch_variant<0, false, 8, 3>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
+        }
+        if (!ep.out_f32) return cudaErrorInvalidValue;
+        if (ep.delta_in && K < 2048) return cudaErrorInvalidValue;   // only the serial (long-K) form folds a pending update
         // long K: the mainloop hides a serial single-buffer epilogue and keeps all 6 stages; short K: pipelined, 4 stages
         if (K >= 2048) return launch_variant<0, true, 8, 2>(tmA, tmB, tmC, *tmX, M, N, K, ep, num_sms, stream);
         // short K (proj): the epilogue is the critical path. The serial form is too slow for it even on 16 warps with

@@ -30,6 +30,11 @@ struct GemmEpilogue {
     int fused_residual = 0;
     const float* resid_in = nullptr;  // == the C matrix (row stride N): lets the epilogue prefetch its rows into L2
     float2* stats_out = nullptr;
+    // "Delta" scheme (see gemm_tcgen05.cu, kResid == 3): delta_out = this producer leaves the fp32 master alone: C (bf16)
+    // receives d = colscale * (acc + bias), the bf16 copy (extra map) is read and rewritten as bf16(xb + d), statistics of
+    // that value; delta_in = a pending d (bf16 [M, N]) that this (fp32, long-K) producer adds on top of x_old.
+    int delta_out = 0;
+    const __nv_bfloat16* delta_in = nullptr;
 };
 
 // ---- TMA descriptors (host) -------------------------------------------------------------------------------------
