@@ -16,7 +16,7 @@ def __getattr__(name):  # torch-dependent pieces are imported lazily so config/s
     if name == "ClipScorer":
         from .scoring import ClipScorer
         return ClipScorer
-    if name in ("metrics", "sharding", "tiling", "llm", "llm_glue", "scoring", "sampling"):
+    if name in ("metrics", "sharding", "tiling", "llm", "llm_glue", "scoring", "sampling", "slowfast"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name in ("install", "refresh", "uninstall"):

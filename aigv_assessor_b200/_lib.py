@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libaigv_b200.so")
 SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention2_tcgen05.cu", "rowops.cu", "preprocess.cu",
-           "llm_glue.cu", "llm_prefill.cu"]
+           "llm_glue.cu", "llm_prefill.cu", "motion_conv.cu"]
 HEADERS = ["kernels.h", "ptx.cuh", os.path.join("..", "..", "include", "aigv_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-t", "0",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -143,6 +143,14 @@ SIGNATURES = {
     "aigv_llm_copy_residual": (C.c_int, [_P, _P, _P]),
     "aigv_rope": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_attention_gqa": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
+    "aigv_im2col3d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "aigv_gemm_ex": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "aigv_maxpool3d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, _P]),
+    "aigv_add_relu": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
+    "aigv_slowfast_tail": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, _P]),
     "aigv_layernorm": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "aigv_rmsnorm_inplace": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_im2col": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -87,6 +87,10 @@ __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const Ge
             x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
         }
     }
+    if (kAct == 0 && ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
     if (kAct == 1) {
 #pragma unroll
 #ifdef AIGV_GELU_AS7126  // the older Abramowitz-Stegun 7.1.26 form (18 issue slots per pair; fc1 2.4% slower)

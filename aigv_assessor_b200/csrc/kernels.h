@@ -15,6 +15,7 @@ struct GemmEpilogue {
     int accumulate = 0;               // fp32 only: C += result (TMA reduce-add; the in-place residual stream)
     int gelu = 0;                     // exact erf GELU after bias
     int m_fast = 0;                   // set by launch_gemm: tile order with M fastest (W much larger than L2, small A)
+    int relu = 0;                     // ReLU after bias (plain epilogues only)
     int swiglu = 0;                   // bf16 only: W interleaves (gate, up) rows; C[M, N/2] = silu(acc[2i]) * acc[2i+1]
     // LayerNorm fusion, consumer side: A was the un-normalised activation (bf16) and W carries gamma;
     //   out = rstd[m] * (acc - mean[m] * ln_wsum[n]) + bias[n]  with mean/rstd from ln_stats[m] = (sum, sum of squares).

@@ -8,9 +8,10 @@ modeling_internvl_chat.py:306-488) composed from this library's CUDA pieces:
     hidden --mlpscore--> score1                                aigv_mlpscore          (eval2 :475)
     answer-span logits --argmax--> 'logit'                     aigv_llm_logits_rows   (eval2 :488; stage1_eval.py:928-929)
 
-What stays with the caller: the SlowFast trunk (eval2 :97-174; pytorchvideo hub weights) that turns the clip's frames into
-one 2304-vector -- pass its output as ``motion_features`` -- tokenisation, and the loss / label bookkeeping of training.
-Inference only; no CPU path.
+    pixel_values --SlowFast-R50 trunk--> 2304 motion features    slowfast.SlowFastTrunk (eval2 :136-193, 337-343), when the state
+                                                                 dict carries ``slowfast_model.*``; else pass ``motion_features``
+
+What stays with the caller: tokenisation and the loss / label bookkeeping of training. Inference only; no CPU path.
 """
 from __future__ import annotations
 
@@ -82,15 +83,24 @@ class ClipScorer:
             self.motion = MotionMlp(sd, self.device)
             self.head = llm_glue.MlpScoreHead(sd, self.device)
             self.tok = torch.as_tensor(sd["language_model.model.tok_embeddings.weight"]).to(self.device).to(torch.bfloat16).contiguous()
+            self.slowfast = None
+            if any(k.startswith("slowfast_model.") for k in sd):
+                from .slowfast import SlowFastTrunk
+                self.slowfast = SlowFastTrunk(sd, device=self.device)
 
     @torch.no_grad()
-    def forward(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, motion_features: torch.Tensor,
+    def forward(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, motion_features: torch.Tensor | None = None,
                 n_answer: int = 48) -> dict:
         """pixel_values bf16 [B*T, 3, 448, 448]; input_ids int64 [B, N]; motion_features [B, 2304] (the SlowFast output,
-        eval2 :343). Returns what the eval scripts read from the reference's forward: 'score1' fp32 [B] and 'logit', the
+        eval2 :343) or None to run this library's trunk on pixel_values. Returns what the eval scripts read from the reference's forward: 'score1' fp32 [B] and 'logit', the
         argmax of the last n_answer shifted logits (stage1_eval.py:928-929 slices exactly that tail), plus 'hidden' =
         hidden_states[-1][:, -4]."""
-        vit = self.vision.extract_feature(pixel_values.to(self.device))
+        pixel_values = pixel_values.to(self.device)
+        if motion_features is None:
+            if self.slowfast is None:
+                raise ValueError("no slowfast_model.* weights were given: pass motion_features")
+            motion_features = self.slowfast(pixel_values, input_ids.shape[0])
+        vit = self.vision.extract_feature(pixel_values)
         mot = self.motion(motion_features.to(self.device))
         x = llm_glue.splice_tokens(input_ids.to(self.device), self.tok, vit, mot, self.img_context_token_id)
         hid, arg, logits = self.language.stage2_tail(x, n_answer=n_answer)
@@ -99,7 +109,7 @@ class ClipScorer:
 
     __call__ = forward
 
-    def score_frames(self, frames_u8: torch.Tensor, input_ids: torch.Tensor, motion_features: torch.Tensor) -> torch.Tensor:
+    def score_frames(self, frames_u8: torch.Tensor, input_ids: torch.Tensor, motion_features: torch.Tensor | None = None) -> torch.Tensor:
         """uint8 frames [T, H, W, 3] of ONE clip (decord layout) -> score1 [1]: front end + forward."""
         pv, _ = self.vision.preprocess_frames(frames_u8, max_num=1)
         return self.forward(pv, input_ids, motion_features)["score1"]

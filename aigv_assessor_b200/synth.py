@@ -223,3 +223,22 @@ def make_clip_prompt(n_frames: int, tokens_per_frame: int = 256, n_text: int = 4
     ids += [IMG_START_ID, IMG_CONTEXT_ID, IMG_END_ID]
     ids += [int(t) for t in rng.integers(20, vocab_size, size=n_text)]
     return np.asarray([ids], dtype=np.int64)
+
+
+def make_slowfast_weights(seed: int = 0) -> dict[str, np.ndarray]:
+    """Seeded stand-in for pytorchvideo's slowfast_r50 checkpoint (absent here): He-scaled conv weights, BatchNorm
+    statistics around identity (gamma ~ 1, beta ~ 0, running_mean ~ 0, running_var ~ 1) so activations stay O(1) through the
+    50 layers. Names / shapes: aigv_assessor_b200.slowfast.layer_table()."""
+    from .slowfast import layer_table
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: dict[str, np.ndarray] = {}
+    for wname, nname, shape in layer_table():
+        fan_in = shape[1] * shape[2] * shape[3] * shape[4]
+        gain = 1.0 if wname.endswith("conv_c.weight") or "branch1" in wname else np.sqrt(2.0)
+        sd[wname] = bf16_round((gain / np.sqrt(fan_in) * rng.standard_normal(size=shape)).astype(np.float32))
+        c = shape[0]
+        sd[nname + ".weight"] = (1.0 + 0.1 * rng.standard_normal(size=(c,))).astype(np.float32)
+        sd[nname + ".bias"] = (0.05 * rng.standard_normal(size=(c,))).astype(np.float32)
+        sd[nname + ".running_mean"] = (0.05 * rng.standard_normal(size=(c,))).astype(np.float32)
+        sd[nname + ".running_var"] = (1.0 + 0.1 * rng.random(size=(c,))).astype(np.float32)
+    return sd

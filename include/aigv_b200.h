@@ -212,6 +212,31 @@ int aigv_rope(void* qkv_bf16, int B, int N, int heads, int kv_heads, int head_di
 int aigv_attention_gqa(const void* qkv_bf16, void* out_bf16, int B, int N, int heads, int kv_heads, int head_dim,
                        float scale, int causal, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Motion branch: per-op entry points from which aigv_assessor_b200/slowfast.py assembles the
+ * SlowFast-R50 trunk the reference calls (eval2 modeling_internvl_chat.py:136-193 -> pytorchvideo slowfast_r50 blocks 0-4 +
+ * pools). Activations are channels-last bf16 [n, t, h, w, c]; BatchNorm is folded into weights / bias by the host.
+ *   aigv_im2col3d     Conv3d's patch gather: out[pos, (dt, dh, dw, c)] (row stride kpad, zero padded); element strides
+ *                     of the input are explicit, so it also reads the NCHW pixel_values for the stems
+ *   aigv_gemm_ex      out[M, N] (row stride ldc) = act(A[M, K] (row stride lda) W[N, K]^T + bias). W / bias hold n_pad >= N
+ *                     rows (zero padded by the caller): with n_pad % 32 == 0, K % 8 == 0, N % 8 == 0 and 16-byte alignment the
+ *                     tcgen05 kernel computes n_pad columns and its TMA store is clipped to the N real ones; otherwise a
+ *                     CUDA-core kernel runs
+ *   aigv_maxpool3d    MaxPool3d((1,kh,kw), (1,sh,sw), (0,ph,pw)) of the stems (n_t = n * t frames), output row stride ldo
+ *   aigv_add_relu     residual join: out[r, :C] (row stride ldo) = relu(a[r, :] + b[r, :])
+ *   aigv_slowfast_tail  repeat_interleave(rep) along t + AvgPool3d((kt,kh,kw), stride 1) + AdaptiveAvgPool3d(1)
+ *                     (eval2 :183-189) -> out fp32 [n, out_ld] columns [out_col, out_col + C) */
+int aigv_im2col3d(const void* in_bf16, void* out_bf16, int n, int T, int H, int W, int C, int64_t s_n, int64_t s_t,
+                  int64_t s_h, int64_t s_w, int64_t s_c, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph,
+                  int pw, int kpad, void* stream);
+int aigv_gemm_ex(const void* a_bf16, int lda, const void* w_bf16, const float* bias, void* out_bf16, int ldc, int M, int N,
+                 int n_pad, int K, int relu, void* stream);
+int aigv_maxpool3d(const void* in_bf16, void* out_bf16, int n_t, int H, int W, int C, int kh, int kw, int sh, int sw, int ph,
+                   int pw, int ldo, void* stream);
+int aigv_add_relu(const void* a_bf16, const void* b_bf16, void* out_bf16, int64_t rows, int C, int ldo, void* stream);
+int aigv_slowfast_tail(const void* x_bf16, float* out_f32, int n, int T, int H, int W, int C, int ld, int rep, int kt, int kh,
+                       int kw, int out_ld, int out_col, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -232,3 +232,34 @@ def test_clip_prompt_has_the_call_shape_of_the_video_prompt():
     ids = synth.make_clip_prompt(8)
     assert ids.shape == (1, 1 + 8 * 258 + 3 + 40)
     assert int((ids == synth.IMG_CONTEXT_ID).sum()) == 8 * 256 + 1   # 2048 visual slots + the motion slot (eval2 :351-378)
+
+
+def test_slowfast_layer_table_matches_the_oracle_spec_and_synth_weights():
+    """Product (slowfast.layer_table) and oracle (slowfast_oracle.weight_spec) state the trunk independently: same tensors, same
+    shapes; the 2304-wide output is what motion_mlp's LayerNorm takes (eval2 :244)."""
+    from aigv_assessor_b200 import slowfast
+    from oracle import slowfast_oracle as so
+    spec = {n: s for n, s, _ in so.weight_spec()}
+    names = set()
+    for w, nm, shape in slowfast.layer_table():
+        assert spec[w] == tuple(shape), w
+        names.add(w)
+        for suf in (".weight", ".bias", ".running_mean", ".running_var"):
+            assert spec[nm + suf] == (shape[0],)
+            names.add(nm + suf)
+    assert names == set(spec) and len(slowfast.layer_table()) == 110
+    assert slowfast.FEATURES == 2304
+    sd = synth.make_slowfast_weights(seed=3)
+    assert set(sd) == set(spec) and all(tuple(sd[k].shape) == spec[k] for k in spec)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.AigvError):
+            slowfast.SlowFastTrunk(sd)
+
+
+def test_slowfast_oracle_call_shape():
+    """pack_pathways = the reference's pack_pathway_output (eval2 :95-133): fast = all frames, slow = linspace pick of T // 4."""
+    from oracle import slowfast_oracle as so
+    pv = torch.arange(2 * 8, dtype=torch.float32).view(16, 1, 1, 1).expand(16, 3, 2, 2).contiguous()
+    slow, fast = so.pack_pathways(pv, 2)
+    assert slow.shape == (2, 3, 2, 2, 2) and fast.shape == (2, 3, 8, 2, 2)
+    assert slow[0, 0, :, 0, 0].tolist() == [0.0, 7.0] and slow[1, 0, :, 0, 0].tolist() == [8.0, 15.0]

@@ -7,7 +7,7 @@ src=aigv_assessor_b200/csrc
 obj=/tmp/aigv_variant_$name
 mkdir -p $obj variants
 pids=()
-for f in api gemm_tcgen05 attention2_tcgen05 rowops preprocess llm_glue llm_prefill; do
+for f in api gemm_tcgen05 attention2_tcgen05 rowops preprocess llm_glue llm_prefill motion_conv; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DAIGV_SRC_HASH=\"variant-$name\" "$@" -c $src/$f.cu -o $obj/$f.o &
   pids+=($!)
 done
