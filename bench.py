@@ -497,15 +497,19 @@ def run_native(args, rank, local_rank, world, out):
                 eng_s = VisionEngine(cfg_s, max_tiles=8, device=dev).load_state_dict(synth.make_weights(cfg_s, seed=3))
                 hsd = synth.make_head_weights(seed=5)
                 head = llm_glue.MlpScoreHead(hsd, dev)
+                from aigv_assessor_b200.scoring import MotionMlp
+                from aigv_assessor_b200.slowfast import SlowFastTrunk
+                trunk = SlowFastTrunk(synth.make_slowfast_weights(seed=6), device=dev)
+                motion = MotionMlp(hsd, dev)
                 tok = (torch.randn((c7["vocab_size"], c7["hidden_size"]), device=dev) * 0.5).to(torch.bfloat16)
                 ids = torch.from_numpy(synth.make_clip_prompt(8, seed=1, vocab_size=c7["vocab_size"])).to(dev)
-                mot = (torch.randn((1, c7["hidden_size"]), device=dev) * 0.5).to(torch.bfloat16)
                 clip_host = torch.randint(0, 256, (8, fh, fw, 3), dtype=torch.uint8).pin_memory()
 
                 def clip_to_score():
                     fr = clip_host.to(dev, non_blocking=True)
                     pv8, _ = eng_s.preprocess_frames(fr, max_num=1)
                     vit = eng_s.extract_feature(pv8)
+                    mot = motion(trunk(pv8, 1))          # SlowFast-R50 trunk + motion_mlp on the same frames (eval2 :337-345)
                     xs = llm_glue.splice_tokens(ids, tok, vit, mot, synth.IMG_CONTEXT_ID, check=False)
                     lm.prefill(xs)
                     sc, _ = head(lm.hidden_rows([n_tok - 4]))
@@ -517,10 +521,10 @@ def run_native(args, rank, local_rank, world, out):
                     "clips_per_s": world / ms_c * 1e3, "ms_per_clip": ms_c, "frames_per_clip": 8, "finite": bool(np.isfinite(sc0)),
                     "h2d_bytes_per_clip": int(clip_host.numel()), "d2h_bytes_per_clip": 4,
                     "note": "one 8-frame 1280x720 uint8 clip on the host -> H2D -> aigv_preprocess_u8 -> InternViT-300M + projector "
-                            "(4096 wide) -> aigv_splice_tokens -> InternLM2-7B prefill (2108 tokens) -> final norm on row -4 -> "
-                            "aigv_mlpscore -> score on the host; synchronous per clip (no overlap between clips); SlowFast excluded"}
+                            "(4096 wide) + SlowFast-R50 trunk + motion_mlp -> aigv_splice_tokens -> InternLM2-7B prefill (2108 tokens) -> "
+                            "final norm on row -4 -> aigv_mlpscore -> score on the host; synchronous per clip (no overlap between clips)"}
                 eng_s.close()
-                del eng_s, tok
+                del eng_s, tok, trunk
             except Exception as e:
                 extra["clip_to_score_7b"] = {"unavailable": repr(e)[:300]}
             lm.close()
