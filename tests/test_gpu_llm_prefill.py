@@ -207,3 +207,37 @@ def test_clip_scorer_reproduces_the_reference_forward(golden_dir):
         assert d <= 0.02
         assert same[decided].all()
         del scorer
+
+
+def test_clip_scorer_from_a_model_shaped_object(golden_dir):
+    """ClipScorer.from_model on an object shaped like the eval2 InternVLChatModel (vision_model.config, mlp1, language_model.config,
+    state_dict(), img_context_token_id): the configs are read off the model, the result equals the explicitly built scorer."""
+    import types
+    from aigv_assessor_b200.config import VisionPathConfig
+    from aigv_assessor_b200.scoring import ClipScorer
+    meta, sd_head, g = _head_case(golden_dir, "tiny")
+    cfg = VisionPathConfig(**meta["vis_cfg"])
+    sd = dict(synth.make_weights(cfg, seed=meta["seeds"]["vis"]))
+    sd.update(sd_head)
+    llm = meta["llm"]
+    model = types.SimpleNamespace()
+    model.vision_model = types.SimpleNamespace(config=types.SimpleNamespace(
+        hidden_size=cfg.hidden_size, num_attention_heads=cfg.num_heads, intermediate_size=cfg.intermediate_size,
+        num_hidden_layers=cfg.num_layers, image_size=cfg.image_size, patch_size=cfg.patch_size, qkv_bias=cfg.qkv_bias,
+        qk_normalization=cfg.qk_normalization, norm_type=cfg.norm_type, layer_norm_eps=cfg.layer_norm_eps))
+    model.mlp1 = types.SimpleNamespace(state_dict=lambda: {"3.weight": torch.from_numpy(sd["mlp1.3.weight"])})
+    model.language_model = types.SimpleNamespace(config=types.SimpleNamespace(
+        hidden_size=llm["hidden_size"], num_hidden_layers=llm["num_hidden_layers"], num_attention_heads=llm["num_attention_heads"],
+        num_key_value_heads=llm["num_key_value_heads"], intermediate_size=llm["intermediate_size"], vocab_size=llm["vocab_size"],
+        rms_norm_eps=llm["rms_norm_eps"], rope_theta=llm["rope_theta"], max_position_embeddings=llm["max_position_embeddings"]))
+    model.state_dict = lambda: {k: torch.from_numpy(v) for k, v in sd.items()}
+    model.img_context_token_id = synth.IMG_CONTEXT_ID
+    pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["seeds"]["x"])
+    ids = synth.make_clip_prompt(meta["n_frames"], seed=meta["seeds"]["ids"], vocab_size=llm["vocab_size"])
+    scorer = ClipScorer.from_model(model, max_tiles=8, max_tokens=ids.shape[1])
+    feat = ho.fake_slowfast(torch.from_numpy(pv), 1)
+    out = scorer(torch.from_numpy(pv).to(torch.bfloat16).cuda(), torch.from_numpy(ids).cuda(), feat.cuda())
+    torch.cuda.synchronize()
+    assert abs(float(out["score1"][0]) - float(g["score1"][0])) <= 0.02
+    with pytest.raises(ValueError):
+        scorer(torch.from_numpy(pv).to(torch.bfloat16).cuda(), torch.from_numpy(ids).cuda())   # no slowfast_model.* weights, no features
