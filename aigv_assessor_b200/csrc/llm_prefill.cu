@@ -335,6 +335,9 @@ void aigv_llm_destroy(aigv_llm_handle* h) {
     cudaDeviceSynchronize();
     for (void* q : h->allocs)
         if (q) cudaFree(q);
+    for (auto& w : h->layers)   // raw copies of weights that were set but never finalized
+        for (void* q : {w.raw_wqkv, w.raw_w1, w.raw_w3})
+            if (q) cudaFree(q);
     delete h;
 }
 
