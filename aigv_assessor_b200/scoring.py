@@ -114,6 +114,13 @@ class ClipScorer:
         pv, _ = self.vision.preprocess_frames(frames_u8, max_num=1)
         return self.forward(pv, input_ids, motion_features)["score1"]
 
+    def score_video(self, path: str, input_ids: torch.Tensor, num_segments: int = 8, bound=None) -> torch.Tensor:
+        """Video file -> score1 [1]: sampling.load_video (CPU decode of the sampled frames, as the reference does) + score_frames;
+        needs the motion trunk's weights (or use score_frames with your own motion features)."""
+        from . import sampling
+        frames, _ = sampling.load_video(path, num_segments=num_segments, bound=bound)
+        return self.score_frames(frames, input_ids)
+
     @classmethod
     def from_model(cls, model, **kw) -> "ClipScorer":
         """Build from a live eval2-style InternVLChatModel (reads its state dict and configs; LoRA in the vision tower is

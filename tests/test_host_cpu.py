@@ -263,3 +263,35 @@ def test_slowfast_oracle_call_shape():
     slow, fast = so.pack_pathways(pv, 2)
     assert slow.shape == (2, 3, 2, 2, 2) and fast.shape == (2, 3, 8, 2, 2)
     assert slow[0, 0, :, 0, 0].tolist() == [0.0, 7.0] and slow[1, 0, :, 0, 0].tolist() == [8.0, 15.0]
+
+
+def test_load_video_decodes_exactly_the_sampled_frames(tmp_path):
+    """sampling.load_video on a synthetic MJPG clip: the sampled frames equal the same frames of a sequential decode, in RGB."""
+    cv2 = pytest.importorskip("cv2")
+    from aigv_assessor_b200 import sampling
+    path = str(tmp_path / "clip.avi")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 24.0, (96, 64))
+    if not w.isOpened():
+        pytest.skip("no MJPG encoder in this OpenCV build")
+    rng = np.random.Generator(np.random.PCG64(0))
+    for i in range(40):
+        f = np.zeros((64, 96, 3), np.uint8)
+        f[..., 0], f[..., 1], f[..., 2] = 5 * i, 255 - 5 * i, rng.integers(0, 255)   # BGR planes that identify the frame
+        w.write(f)
+    w.release()
+    cap = cv2.VideoCapture(path)
+    seq = []
+    while True:
+        ok, bgr = cap.read()
+        if not ok:
+            break
+        seq.append(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB))
+    cap.release()
+    assert len(seq) == 40
+    frames, idx = sampling.load_video(path, num_segments=8)
+    assert idx.tolist() == sampling.frame_indices(40, 24.0, 8).tolist()
+    assert frames.shape == (8, 64, 96, 3) and frames.dtype == torch.uint8
+    for k, i in enumerate(idx.tolist()):
+        assert np.array_equal(frames[k].numpy(), seq[i]), (k, i)
+    with pytest.raises(ValueError):
+        sampling.load_video(str(tmp_path / "missing.mp4"))
