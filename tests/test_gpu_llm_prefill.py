@@ -241,3 +241,23 @@ def test_clip_scorer_from_a_model_shaped_object(golden_dir):
     assert abs(float(out["score1"][0]) - float(g["score1"][0])) <= 0.02
     with pytest.raises(ValueError):
         scorer(torch.from_numpy(pv).to(torch.bfloat16).cuda(), torch.from_numpy(ids).cuda())   # no slowfast_model.* weights, no features
+
+
+@pytest.mark.parametrize("B,N,hidden,nh,nkv,inter", [(3, 77, 2048, 16, 8, 8192), (1, 1, 2048, 16, 8, 2048), (2, 130, 512, 8, 8, 1024),
+                                                     (1, 260, 256, 4, 1, 512)])
+def test_prefill_other_widths_and_tiny_prompts(B, N, hidden, nh, nkv, inter):
+    """InternLM2-1.8B's width (2048, 16/8 heads of 128), multi-head without grouping, a single kv head of 64, one-token prompts."""
+    llm = dict(hidden_size=hidden, num_hidden_layers=2, num_attention_heads=nh, num_key_value_heads=nkv, intermediate_size=inter,
+               vocab_size=96, rms_norm_eps=1e-5, rope_theta=1e6, max_position_embeddings=4096)
+    sd = synth.make_head_weights(seed=hidden + N, llm=llm)
+    g = torch.Generator().manual_seed(N)
+    emb = (torch.randn((B, N, hidden), generator=g) * 0.5).to(torch.bfloat16)
+    eng = L.LanguageEngine(llm, max_tokens=B * N).load_state_dict(sd)
+    eng.prefill(emb.cuda())
+    rows = sorted({0, N - 1, (B - 1) * N, B * N - 1})
+    hid, logits = eng.hidden_rows(rows).cpu(), eng.logits_rows(rows).cpu()
+    torch.cuda.synchronize()
+    ref_h, ref_l = ho.internlm2(emb.float(), ho.to_torch(sd), llm)
+    e_h = vo.error_metrics(hid.numpy(), ref_h.reshape(B * N, -1)[rows].numpy())
+    e_l = vo.error_metrics(logits.numpy(), ref_l.reshape(B * N, -1)[rows].numpy())
+    assert e_h[0] < 2e-2 and e_l[0] < 2e-2, (e_h, e_l)
