@@ -20,7 +20,9 @@ restated here is pytorchvideo's PUBLISHED architecture for ``create_slowfast`` w
 State-dict names follow pytorchvideo's module tree under the reference's wrapper (``slowfast_model.feature_extraction.<i>.``).
 Anchors that ARE the reference's: the call shape (pack_pathway_output's linspace pick of T//4 slow frames, the tail, the
 2304-wide output that motion_mlp's LayerNorm(2304) consumes, eval2 :244-249). The CUDA path (aigv_assessor_b200/slowfast.py)
-is tested against THIS restatement, so a mistake in the restated architecture would not be caught: hence "unpinned".
+is tested against THIS restatement, so a mistake in the restated architecture would not be caught: hence "unpinned". One
+weak anchor exists: with the 400-class head the reference drops, the restated network has 34 566 488 learnable parameters =
+the 34.57 M pytorchvideo's model zoo lists for slowfast_r50 (tests/test_host_cpu.py).
 """
 from __future__ import annotations
 

@@ -295,3 +295,12 @@ def test_load_video_decodes_exactly_the_sampled_frames(tmp_path):
         assert np.array_equal(frames[k].numpy(), seq[i]), (k, i)
     with pytest.raises(ValueError):
         sampling.load_video(str(tmp_path / "missing.mp4"))
+
+
+def test_slowfast_restatement_reproduces_the_published_parameter_count():
+    """A weak anchor for the unpinned motion-trunk oracle: the restated architecture + the Kinetics head the reference drops
+    (Linear(2304, 400)) has 34 566 488 learnable parameters = the 34.57 M pytorchvideo's model zoo lists for slowfast_r50 8x8."""
+    from oracle import slowfast_oracle as so
+    learnable = sum(int(np.prod(s)) for _, s, k in so.weight_spec() if k in ("conv", "bn_w", "bn_b"))
+    assert learnable == 33_644_488
+    assert round((learnable + 2304 * 400 + 400) / 1e6, 2) == 34.57
