@@ -21,8 +21,10 @@ State-dict names follow pytorchvideo's module tree under the reference's wrapper
 Anchors that ARE the reference's: the call shape (pack_pathway_output's linspace pick of T//4 slow frames, the tail, the
 2304-wide output that motion_mlp's LayerNorm(2304) consumes, eval2 :244-249). The CUDA path (aigv_assessor_b200/slowfast.py)
 is tested against THIS restatement, so a mistake in the restated architecture would not be caught: hence "unpinned". One
-weak anchor exists: with the 400-class head the reference drops, the restated network has 34 566 488 learnable parameters =
-the 34.57 M pytorchvideo's model zoo lists for slowfast_r50 (tests/test_host_cpu.py).
+Two weak anchors exist (tests/test_host_cpu.py): with the 400-class head the reference drops, the restated network has
+34 566 488 learnable parameters = the 34.57 M pytorchvideo's model zoo lists for slowfast_r50, and 65.71 G multiply-accumulates
+for the Kinetics 8x8 setting (8 / 32 frames, 256 x 256) = the published 65.71 GFLOPs: widths, kernel sizes, strides and the
+fusion are right; the order of BN / ReLU and the paddings are not covered by them.
 """
 from __future__ import annotations
 

@@ -304,3 +304,36 @@ def test_slowfast_restatement_reproduces_the_published_parameter_count():
     learnable = sum(int(np.prod(s)) for _, s, k in so.weight_spec() if k in ("conv", "bn_w", "bn_b"))
     assert learnable == 33_644_488
     assert round((learnable + 2304 * 400 + 400) / 1e6, 2) == 34.57
+
+
+def test_slowfast_restatement_reproduces_the_published_flops():
+    """Second weak anchor: multiply-accumulates of the restated network for the Kinetics 8x8 setting (slow 8 / fast 32 frames,
+    256 x 256 crop, 400-class head) = 65.71 G, the figure the SlowFast paper and pytorchvideo's model zoo list for R50 8x8."""
+    from aigv_assessor_b200 import slowfast as sf
+
+    def out(n, k, s, p):
+        return (n + 2 * p - k) // s + 1
+
+    H, Ts, Tf = 256, 8, 32
+    macs = 0
+    Hs = out(H, 7, 2, 3)
+    macs += 64 * 3 * 1 * 7 * 7 * Ts * Hs * Hs + 8 * 3 * 5 * 7 * 7 * Tf * Hs * Hs
+    cur = out(Hs, 3, 2, 1)
+    fast_dims, slow_dims = (8, 32, 64, 128), (64, 256, 512, 1024)
+    macs += 16 * 8 * 7 * Ts * cur * cur
+    for s in range(4):
+        for P, din, T in ((sf.SLOW, slow_dims[s] + 2 * fast_dims[s], Ts), (sf.FAST, fast_dims[s], Tf)):
+            h = cur
+            for b in range(sf.DEPTHS[s]):
+                cin = din if b == 0 else P["out"][s]
+                st = sf.SPATIAL_STRIDE[s] if b == 0 else 1
+                ho = out(h, 3, st, 1) if st > 1 else h
+                if b == 0:
+                    macs += P["out"][s] * cin * T * ho * ho
+                macs += P["inner"][s] * cin * P["kt"][s] * T * h * h + P["inner"][s] * P["inner"][s] * 9 * T * ho * ho
+                macs += P["out"][s] * P["inner"][s] * T * ho * ho
+                h = ho
+        cur = h
+        if s < 3:
+            macs += 2 * sf.FAST["out"][s] * sf.FAST["out"][s] * 7 * Ts * cur * cur
+    assert round((macs + 2304 * 400) / 1e9, 2) == 65.71
