@@ -87,6 +87,21 @@ class ClipScorer:
             if any(k.startswith("slowfast_model.") for k in sd):
                 from .slowfast import SlowFastTrunk
                 self.slowfast = SlowFastTrunk(sd, device=self.device)
+            self._side = None
+            self.check_splice = True   # read the splice kernel's error flag back (one host sync per call)
+
+    @classmethod
+    def from_parts(cls, vision: VisionEngine, language: LanguageEngine, motion: MotionMlp, head, tok_embeddings: torch.Tensor,
+                   img_context_token_id: int, slowfast=None) -> "ClipScorer":
+        """Assemble from engines that already hold their weights (e.g. generated on the device)."""
+        self = cls.__new__(cls)
+        self.device = vision.device
+        self.img_context_token_id = int(img_context_token_id)
+        self.vision, self.language, self.motion, self.head, self.slowfast = vision, language, motion, head, slowfast
+        self.tok = tok_embeddings
+        self._side = None
+        self.check_splice = True
+        return self
 
     @torch.no_grad()
     def forward(self, pixel_values: torch.Tensor, input_ids: torch.Tensor, motion_features: torch.Tensor | None = None,
@@ -99,10 +114,22 @@ class ClipScorer:
         if motion_features is None:
             if self.slowfast is None:
                 raise ValueError("no slowfast_model.* weights were given: pass motion_features")
-            motion_features = self.slowfast(pixel_values, input_ids.shape[0])
-        vit = self.vision.extract_feature(pixel_values)
-        mot = self.motion(motion_features.to(self.device))
-        x = llm_glue.splice_tokens(input_ids.to(self.device), self.tok, vit, mot, self.img_context_token_id)
+            # the motion branch (215 small, latency-bound launches as one CUDA graph + motion_mlp) runs on a side stream next to
+            # the ViT: the two only meet at the splice
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                mot = self.motion(self.slowfast(pixel_values, input_ids.shape[0]))
+            vit = self.vision.extract_feature(pixel_values)
+            main.wait_stream(self._side)
+            mot.record_stream(main)
+        else:
+            vit = self.vision.extract_feature(pixel_values)
+            mot = self.motion(motion_features.to(self.device))
+        x = llm_glue.splice_tokens(input_ids.to(self.device), self.tok, vit, mot, self.img_context_token_id,
+                                   check=getattr(self, "check_splice", True))
         hid, arg, logits = self.language.stage2_tail(x, n_answer=n_answer)
         score, pre = self.head(hid)
         return {"score1": score, "score_pre_relu": pre, "logit": arg, "logits_tail": logits, "hidden": hid}

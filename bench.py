@@ -505,15 +505,15 @@ def run_native(args, rank, local_rank, world, out):
                 ids = torch.from_numpy(synth.make_clip_prompt(8, seed=1, vocab_size=c7["vocab_size"])).to(dev)
                 clip_host = torch.randint(0, 256, (8, fh, fw, 3), dtype=torch.uint8).pin_memory()
 
+                from aigv_assessor_b200.scoring import ClipScorer
+                scorer = ClipScorer.from_parts(eng_s, lm, motion, head, tok, synth.IMG_CONTEXT_ID, slowfast=trunk)
+                scorer.check_splice = False   # the prompt is known good: no extra host sync per clip
+
                 def clip_to_score():
                     fr = clip_host.to(dev, non_blocking=True)
                     pv8, _ = eng_s.preprocess_frames(fr, max_num=1)
-                    vit = eng_s.extract_feature(pv8)
-                    mot = motion(trunk(pv8, 1))          # SlowFast-R50 trunk + motion_mlp on the same frames (eval2 :337-345)
-                    xs = llm_glue.splice_tokens(ids, tok, vit, mot, synth.IMG_CONTEXT_ID, check=False)
-                    lm.prefill(xs)
-                    sc, _ = head(lm.hidden_rows([n_tok - 4]))
-                    return float(sc[0].item())      # D2H of the score: the step's result reaches the host
+                    out_s = scorer(pv8, ids)                  # ViT || SlowFast trunk + motion_mlp -> splice -> prefill -> heads
+                    return float(out_s["score1"][0].item())   # D2H of the score: the step's result reaches the host
                 for _ in range(2):
                     sc0 = clip_to_score()
                 ms_c = timed(clip_to_score, 5)
