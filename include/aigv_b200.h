@@ -191,7 +191,8 @@ int64_t aigv_llm_launch_count(const aigv_llm_handle* h);
  * model.layers.{i}.attention.wqkv.weight / .attention.wo.weight / .attention_norm.weight / .ffn_norm.weight /
  * .feed_forward.w1.weight / .w2.weight / .w3.weight, model.norm.weight, output.weight (optional: only aigv_llm_logits_rows
  * needs it). Host or device pointer, fp32 or bf16; copied and re-packed (RMSNorm weights folded into wqkv / w1 / w3, w1 and
- * w3 interleaved). Synchronous. */
+ * w3 interleaved) at aigv_llm_finalize_weights, after which the raw copies are dropped: to change a norm weight later, re-set
+ * the matrices it feeds as well and finalize again. Synchronous. */
 int aigv_llm_set_weight(aigv_llm_handle* h, const char* name, const void* ptr, int dtype, const int64_t* shape, int rank);
 int aigv_llm_finalize_weights(aigv_llm_handle* h, void* stream);
 /* The decoder stack on inputs_embeds bf16 [B*N, hidden] (sample-major; = the output of aigv_splice_tokens). The residual
