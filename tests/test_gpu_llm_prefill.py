@@ -261,3 +261,33 @@ def test_prefill_other_widths_and_tiny_prompts(B, N, hidden, nh, nkv, inter):
     e_h = vo.error_metrics(hid.numpy(), ref_h.reshape(B * N, -1)[rows].numpy())
     e_l = vo.error_metrics(logits.numpy(), ref_l.reshape(B * N, -1)[rows].numpy())
     assert e_h[0] < 2e-2 and e_l[0] < 2e-2, (e_h, e_l)
+
+
+def test_prefill_trained_like_statistics(golden_dir):
+    """What trained LLMs look like where the numerics care: massive-activation channels in the residual stream (+-400), peaked
+    attention (wqkv x3), a large-norm first token -- RMSNorm statistics from sum-of-squares slices, the stale-max softmax with
+    causal masking, the SwiGLU epilogue's exponent range."""
+    meta, sd_head, _ = _head_case(golden_dir)
+    llm = dict(meta["llm"])
+    sd = dict(sd_head)
+    for i in range(llm["num_hidden_layers"]):
+        k = f"language_model.model.layers.{i}.attention.wqkv.weight"
+        sd[k] = synth.bf16_round(sd[k] * np.float32(3.0))
+    g = torch.Generator().manual_seed(23)
+    B, N, H = 1, 700, llm["hidden_size"]
+    emb = torch.randn((B, N, H), generator=g) * 0.5
+    emb[:, :, 7] += 400.0
+    emb[:, :, 1033] -= 250.0
+    emb[:, 0, :] *= 20.0
+    emb = emb.to(torch.bfloat16)
+    eng = L.LanguageEngine(llm, max_tokens=B * N).load_state_dict(sd)
+    eng.prefill(emb.cuda())
+    rows = [0, 1, 350, N - 4, N - 1]
+    hid, logits = eng.hidden_rows(rows).cpu(), eng.logits_rows(rows).cpu()
+    torch.cuda.synchronize()
+    ref_h, ref_l = ho.internlm2(emb.float(), ho.to_torch(sd), llm)
+    e_h = vo.error_metrics(hid.numpy(), ref_h[0, rows].numpy())
+    e_l = vo.error_metrics(logits.numpy(), ref_l[0, rows].numpy())
+    print(f"trained-like prefill: hidden rows e_max/e_l2 {e_h} logits {e_l}; |hidden| max {float(ref_h.abs().max()):.1f}")
+    assert torch.isfinite(hid).all() and torch.isfinite(logits).all()
+    assert e_h[0] < 2e-2 and e_l[0] < 2e-2
