@@ -258,9 +258,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 __syncwarp();
                 issue_xload(0);
                 if (kResid == 3 && SLICE_COLS > 64) issue_xload(64);   // both 64-column groups of the slice, a mainloop ahead
-                // x_old is streamed from HBM (the residual stream is 4 B x M x N, far beyond L2): pull this warp's rows of
-                // the NEXT tile into L2 now, a whole mainloop ahead of the TMA fetches that will want them (and the
-                // current tile's rows for the first tile of this CTA pair).
+                // x_old is streamed from HBM (the residual stream is 4 B x M x N, far beyond L2). Optional L2 prefetches of this
+                // warp's rows (both measured and off by default, see the two macros below).
                 auto prefetch_rows = [&](int tl) {
                     const int mb = ep.m_fast ? tl % num_m : tl / num_n, nb = ep.m_fast ? tl / num_m : tl % num_n;
                     const int r0 = mb * 2 * BM + static_cast<int>(rank) * BM + quad * 32 + lane;
@@ -276,7 +275,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (tile == pair) prefetch_rows(tile);
                     if (tile + num_pairs < num_tiles) prefetch_rows(tile + num_pairs);
                 } else if (kResid == 2) {
+#ifdef AIGV_GEMM_XPREFETCH   // round 1 pulled this tile's x_old rows into L2 here; with the delta scheme it costs 1 % on fc2,
+                             // the 6B tower and the LLM's wo / w2 (same-box A/B, profiles/r2r_xprefetch_ab.txt): off
                     prefetch_rows(tile);
+#endif
                 }
             }
             // LayerNorm-fused consumer: this thread's row statistics (fetched ahead of the accumulator wait)
