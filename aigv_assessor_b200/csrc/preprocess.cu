@@ -111,35 +111,51 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int W, int64_t frame_strid
     }
     __syncthreads();
 
-    // phase B: horizontal taps; items (column, row) in row-fastest order, 256 apart per step: no division in the loop
+    // phase B: horizontal taps. One item = one output column x TWO source rows (rr and rr + nrp): the pair shares the column's
+    // bounds, alignment and tap table loads. Items in row-fastest order, 256 apart per step: no division in the loop.
     const int half = 1 << (PRECISION_BITS - 1);
     {
-        const int step_x = 256 / nrows, step_r = 256 - step_x * nrows;
-        int xx = tid / nrows, rr = tid - xx * nrows;
+        const int nrp = (nrows + 1) >> 1;
+        const int step_x = 256 / nrp, step_r = 256 - step_x * nrp;
+        int xx = tid / nrp, rr = tid - xx * nrp;
         while (xx < nx) {
             const int2 b = __ldg(bx2 + xx);
             const int boff = b.x * 3 - win0;
             const uint32_t* p = srct + rr * sw + (boff >> 2);
+            const uint32_t* q = p + nrp * sw;                       // second row (past the window for the odd last pair: unused)
             const int sh = (boff & 3) * 8;
             const int4* k4 = reinterpret_cast<const int4*>(kxs + xx * ksx);
             const int chunks = (b.y + 3) >> 2;
-            int a0 = half, a1 = half, a2 = half;
-            uint32_t w0 = p[0];
+            int a0 = half, a1 = half, a2 = half, c0 = half, c1 = half, c2 = half;
+            uint32_t w0 = p[0], u0 = q[0];
             for (int c = 0; c < chunks; ++c) {
-                const uint32_t w1 = p[1], w2 = p[2], w3 = p[3];
-                const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
-                               v2 = __funnelshift_r(w2, w3, sh);
                 const int4 k = k4[c];
-                a0 += byte_of<0>(v0) * k.x + byte_of<3>(v0) * k.y + byte_of<2>(v1) * k.z + byte_of<1>(v2) * k.w;
-                a1 += byte_of<1>(v0) * k.x + byte_of<0>(v1) * k.y + byte_of<3>(v1) * k.z + byte_of<2>(v2) * k.w;
-                a2 += byte_of<2>(v0) * k.x + byte_of<1>(v1) * k.y + byte_of<0>(v2) * k.z + byte_of<3>(v2) * k.w;
-                w0 = w3;
+                {
+                    const uint32_t w1 = p[1], w2 = p[2], w3 = p[3];
+                    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
+                                   v2 = __funnelshift_r(w2, w3, sh);
+                    a0 += byte_of<0>(v0) * k.x + byte_of<3>(v0) * k.y + byte_of<2>(v1) * k.z + byte_of<1>(v2) * k.w;
+                    a1 += byte_of<1>(v0) * k.x + byte_of<0>(v1) * k.y + byte_of<3>(v1) * k.z + byte_of<2>(v2) * k.w;
+                    a2 += byte_of<2>(v0) * k.x + byte_of<1>(v1) * k.y + byte_of<0>(v2) * k.z + byte_of<3>(v2) * k.w;
+                    w0 = w3;
+                }
+                {
+                    const uint32_t u1 = q[1], u2 = q[2], u3 = q[3];
+                    const uint32_t v0 = __funnelshift_r(u0, u1, sh), v1 = __funnelshift_r(u1, u2, sh),
+                                   v2 = __funnelshift_r(u2, u3, sh);
+                    c0 += byte_of<0>(v0) * k.x + byte_of<3>(v0) * k.y + byte_of<2>(v1) * k.z + byte_of<1>(v2) * k.w;
+                    c1 += byte_of<1>(v0) * k.x + byte_of<0>(v1) * k.y + byte_of<3>(v1) * k.z + byte_of<2>(v2) * k.w;
+                    c2 += byte_of<2>(v0) * k.x + byte_of<1>(v1) * k.y + byte_of<0>(v2) * k.z + byte_of<3>(v2) * k.w;
+                    u0 = u3;
+                }
                 p += 3;
+                q += 3;
             }
             tmp[rr * TMP_STRIDE + xx] = clip8(a0) | (clip8(a1) << 8) | (clip8(a2) << 16);
+            if (rr + nrp < nrows) tmp[(rr + nrp) * TMP_STRIDE + xx] = clip8(c0) | (clip8(c1) << 8) | (clip8(c2) << 16);
             xx += step_x;
             rr += step_r;
-            if (rr >= nrows) { rr -= nrows; ++xx; }
+            if (rr >= nrp) { rr -= nrp; ++xx; }
         }
     }
     __syncthreads();
