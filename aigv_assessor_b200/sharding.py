@@ -64,3 +64,30 @@ def encode_clips_sharded(engine, clips: Sequence[torch.Tensor], pool: bool = Fal
         local = torch.empty((0, c) if pool else (0, f, c), device=engine.device,
                             dtype=torch.float32 if pool else torch.bfloat16)
     return gather_clip_results(local, len(clips), rank, world)
+
+
+def score_clips_sharded(scorer, clips, input_ids, mos=None, motion_features=None) -> dict:
+    """The sharded counterpart of the stage-2 eval loop (stage2_eval.py:915-975: one forward per video, score1 collected,
+    SRCC / PLCC / KRCC printed at the end): every rank scores its round-robin share of ``clips`` with ``scorer``
+    (scoring.ClipScorer), the scores are all-gathered once, and -- when ``mos`` is given -- the reference's metrics are computed.
+
+    clips: list of pixel_values [frames, 3, 448, 448] (or uint8 frames [frames, H, W, 3]); input_ids: one [1, N] prompt for all
+    clips or a list of them; motion_features: optional list of [1, 2304] (else the scorer's own trunk runs)."""
+    from . import metrics
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    mine = shard_indices(len(clips), rank, world)
+    local = []
+    for i in mine:
+        ids = input_ids[i] if isinstance(input_ids, (list, tuple)) else input_ids
+        mf = None if motion_features is None else motion_features[i]
+        clip = clips[i]
+        if clip.dtype == torch.uint8:
+            clip, _ = scorer.vision.preprocess_frames(clip, max_num=1)
+        local.append(scorer(clip, ids, mf)["score1"].reshape(1).float())
+    local_t = torch.cat(local) if local else torch.empty((0,), dtype=torch.float32, device=scorer.device)
+    scores = gather_clip_results(local_t, len(clips), rank, world)
+    out = {"scores": scores}
+    if mos is not None and len(clips) >= 2:
+        out.update(metrics.correlations(list(mos), scores.cpu().tolist()))
+    return out

@@ -291,3 +291,27 @@ def test_prefill_trained_like_statistics(golden_dir):
     print(f"trained-like prefill: hidden rows e_max/e_l2 {e_h} logits {e_l}; |hidden| max {float(ref_h.abs().max()):.1f}")
     assert torch.isfinite(hid).all() and torch.isfinite(logits).all()
     assert e_h[0] < 2e-2 and e_l[0] < 2e-2
+
+
+def test_sharded_eval_loop_scores_and_metrics(golden_dir):
+    """sharding.score_clips_sharded (world 1): four synthetic clips -> score1 each -> SRCC / PLCC / KRCC as the eval script prints
+    them; clip 0 is the golden clip, so its score is the reference's."""
+    from aigv_assessor_b200 import sharding
+    from aigv_assessor_b200.config import VisionPathConfig
+    from aigv_assessor_b200.scoring import ClipScorer
+    meta, sd_head, g = _head_case(golden_dir, "tiny")
+    cfg = VisionPathConfig(**meta["vis_cfg"])
+    sd = dict(synth.make_weights(cfg, seed=meta["seeds"]["vis"]))
+    sd.update(sd_head)
+    ids = torch.from_numpy(synth.make_clip_prompt(meta["n_frames"], seed=meta["seeds"]["ids"], vocab_size=meta["llm"]["vocab_size"])).cuda()
+    scorer = ClipScorer(sd, cfg, meta["llm"], synth.IMG_CONTEXT_ID, max_tiles=8, max_tokens=ids.shape[1])
+    clips, feats = [], []
+    for k in range(4):
+        pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["seeds"]["x"] + 100 * k)
+        clips.append(torch.from_numpy(pv).to(torch.bfloat16).cuda())
+        feats.append(ho.fake_slowfast(torch.from_numpy(pv), 1).cuda())
+    res = sharding.score_clips_sharded(scorer, clips, ids, mos=[3.0, 2.0, 4.0, 1.0], motion_features=feats)
+    torch.cuda.synchronize()
+    assert res["scores"].shape == (4,) and torch.isfinite(res["scores"]).all()
+    assert abs(float(res["scores"][0]) - float(g["score1"][0])) <= 0.02
+    assert all(-1.0 <= res[k] <= 1.0 for k in ("srcc", "plcc", "krcc"))
