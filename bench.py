@@ -462,7 +462,7 @@ def run_native(args, rank, local_rank, world, out):
             import tools_bench_llm as tbl
             torch.cuda.empty_cache()
             n_tok = 1 + 8 * 258 + 3 + 40      # <s>, 8 x (<img> 256 x <IMG_CONTEXT> </img>), the motion slot, 40 text tokens
-            c7, lm = tbl.build("7b", n_tok)
+            c7, lm = tbl.build("7b", 4 * n_tok)   # workspace for the 4-clip step of config 3 below
             x7 = (torch.randn((1, n_tok, c7["hidden_size"]), device=dev) * 0.5).to(torch.bfloat16)
             tail = list(range(n_tok - 49, n_tok - 1))
 
@@ -494,7 +494,7 @@ def run_native(args, rank, local_rank, world, out):
                 from aigv_assessor_b200 import llm_glue
                 from aigv_assessor_b200.config import VisionPathConfig
                 cfg_s = VisionPathConfig(llm_hidden=c7["hidden_size"])
-                eng_s = VisionEngine(cfg_s, max_tiles=8, device=dev).load_state_dict(synth.make_weights(cfg_s, seed=3))
+                eng_s = VisionEngine(cfg_s, max_tiles=32, device=dev).load_state_dict(synth.make_weights(cfg_s, seed=3))
                 hsd = synth.make_head_weights(seed=5)
                 head = llm_glue.MlpScoreHead(hsd, dev)
                 from aigv_assessor_b200.scoring import MotionMlp
@@ -523,6 +523,28 @@ def run_native(args, rank, local_rank, world, out):
                     "note": "one 8-frame 1280x720 uint8 clip on the host -> H2D -> aigv_preprocess_u8 -> InternViT-300M + projector "
                             "(4096 wide) + SlowFast-R50 trunk + motion_mlp -> aigv_splice_tokens -> InternLM2-7B prefill (2108 tokens) -> "
                             "final norm on row -4 -> aigv_mlpscore -> score on the host; synchronous per clip (no overlap between clips)"}
+                # BASELINE config 3: 32 clips per step over 8 GPUs = 4 clips per GPU per step, one batched forward: 32 tiles through
+                # the front end / ViT / SlowFast trunk, one [4, 2108] prefill, 4 scores back to the host
+                try:
+                    ids4 = ids.repeat(4, 1).contiguous()
+                    clips4_host = torch.randint(0, 256, (32, fh, fw, 3), dtype=torch.uint8).pin_memory()
+
+                    def clips4_to_scores():
+                        fr = clips4_host.to(dev, non_blocking=True)
+                        pv32, _ = eng_s.preprocess_frames(fr, max_num=1)
+                        return scorer(pv32, ids4)["score1"].cpu()
+                    for _ in range(2):
+                        sc4 = clips4_to_scores()
+                    ms_c4 = timed(clips4_to_scores, 3)
+                    extra["config3_clips_to_score_7b"] = {
+                        "clips_per_s": world * 4 / ms_c4 * 1e3, "ms_per_step": ms_c4, "clips_per_step_per_gpu": 4,
+                        "ms_per_clip": ms_c4 / 4, "finite": bool(torch.isfinite(sc4).all()), "scores_per_step": int(sc4.numel()),
+                        "h2d_bytes_per_step": int(clips4_host.numel()), "d2h_bytes_per_step": 4 * int(sc4.numel()),
+                        "note": "BASELINE config 3 shape (32 clips per step sharded over 8 GPUs): 4 clips per GPU in ONE forward -- 32 uint8 "
+                                "720p frames on the host -> H2D -> front end -> InternViT-300M (32 tiles) || SlowFast trunk (4 clips) + "
+                                "motion_mlp -> splice -> InternLM2-7B prefill of [4, 2108] -> mlpscore -> 4 scores on the host"}
+                except Exception as e:
+                    extra["config3_clips_to_score_7b"] = {"unavailable": repr(e)[:300]}
                 eng_s.close()
                 del eng_s, tok, trunk
             except Exception as e:
