@@ -19,6 +19,8 @@
 //   warps 0-15: epilogue of this CTA's 128 rows (warp%4 = TMEM lane quadrant, warp/4 = 64-column slice; 4 warps per
 //   SMSP hide the GELU / TMEM-load latencies); they release the accumulator stage on the leader's barrier (remote arrive)
 //   warp 16: TMA producer, warp 17: MMA issuer
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -65,6 +67,24 @@ struct Cfg {
 // LN fusion: the A operand was the un-normalised activation x (bf16) and W carries gamma, so
 //   LN(x) W^T = rstd * (x W'^T - mean * wsum) + (b + W beta),   wsum[n] = sum_k W'[n,k]
 // with the row's mean / rstd taken from the (sum, sum of squares) the producing GEMM accumulated.
+// Output tile -> (row tile, column tile). group_m = 0: N fastest (a wave shares few A row tiles and the whole, L2-resident W);
+// group_m = G > 0: M fastest inside groups of G row tiles, the groups walked over all of N one after the other (G >= num_m: plain
+// M fastest -- every W tile leaves DRAM once while a small A stays in L2).
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+    if (group_m <= 0) {
+        m_blk = tile / num_n;
+        n_blk = tile - m_blk * num_n;
+        return;
+    }
+    const int per_group = group_m * num_n;
+    const int g = tile / per_group;
+    const int first_m = g * group_m;
+    const int gsz = min(num_m - first_m, group_m);
+    const int in_g = tile - g * per_group;
+    n_blk = in_g / gsz;
+    m_blk = first_m + (in_g - n_blk * gsz);
+}
+
 template <int kAct>   // 0: none, 1: erf GELU, 2: SwiGLU on (gate, up) column pairs (applied by the caller: halves the width)
 __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep, float mean, float rstd) {
     if (ep.ln_stats) {
@@ -173,9 +193,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-            // tile order: N fastest by default (a wave shares few A row-tiles and the whole, L2-resident W); M fastest when
-            // W is far larger than L2 and A is small (LLM prefill shapes): each W tile then leaves DRAM once
-            const int m_blk = ep.m_fast ? tile % num_m : tile / num_n, n_blk = ep.m_fast ? tile / num_m : tile % num_n;
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, ep.group_m, m_blk, n_blk);
             const int row_a = m_blk * 2 * BM + rank * BM;
             const int row_b = n_blk * BN + rank * BNH;
             for (int kb = 0; kb < num_k; ++kb) {
@@ -238,9 +257,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-            // tile order: N fastest by default (a wave shares few A row-tiles and the whole, L2-resident W); M fastest when
-            // W is far larger than L2 and A is small (LLM prefill shapes): each W tile then leaves DRAM once
-            const int m_blk = ep.m_fast ? tile % num_m : tile / num_n, n_blk = ep.m_fast ? tile / num_m : tile % num_n;
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, ep.group_m, m_blk, n_blk);
             const int row0 = m_blk * 2 * BM + rank * BM + quad * 32;
             const int colb = n_blk * BN + slice * SLICE_COLS;
             // kResid: x_old does not depend on the MMAs: start fetching this warp's first staging tile before waiting
@@ -261,7 +279,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // x_old is streamed from HBM (the residual stream is 4 B x M x N, far beyond L2). Optional L2 prefetches of this
                 // warp's rows (both measured and off by default, see the two macros below).
                 auto prefetch_rows = [&](int tl) {
-                    const int mb = ep.m_fast ? tl % num_m : tl / num_n, nb = ep.m_fast ? tl / num_m : tl % num_n;
+                    int mb, nb;
+                    tile_coords(tl, num_m, num_n, ep.group_m, mb, nb);
                     const int r0 = mb * 2 * BM + static_cast<int>(rank) * BM + quad * 32 + lane;
                     const int c0 = nb * BN + slice * SLICE_COLS;
                     if (r0 < M && c0 < N)
@@ -579,9 +598,14 @@ cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     if (tiles < pairs) pairs = tiles;
     GemmEpilogue epk = ep;
     // W beyond what L2 keeps next to the activations, A smaller than W: walk M fastest so every W tile leaves DRAM once
-    // (measured on the 7B w1|w3 GEMM, M = 2108: 2.12 GB of DRAM reads per launch with N fastest against 0.25 GB algorithmic)
+    // (measured on the 7B w1|w3 GEMM, M = 2108: 2.12 GB of DRAM reads per launch with N fastest against 0.25 GB algorithmic).
+    // With many row tiles (several prompts per prefill: A no longer sits in L2 next to the W stream) M goes fastest inside
+    // groups of 16 row tiles (7B w1|w3 at four prompts per prefill: 26.6 against 28.0 ms per prompt; 8: 27.3, 4: 27.8).
     const double w_bytes = 2.0 * N * K, a_bytes = 2.0 * M * K;
-    epk.m_fast = (w_bytes > 48e6 && a_bytes < w_bytes) ? 1 : 0;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
+    static const int group_big = [] { const char* e = getenv("AIGV_GEMM_GROUP_M"); return e ? atoi(e) : 16; }();
+    epk.group_m = 0;
+    if (w_bytes > 48e6 && a_bytes < w_bytes) epk.group_m = (num_m <= 20 || group_big <= 0) ? num_m : group_big;
     kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmX, M, N, K, epk);
     return cudaGetLastError();
 }

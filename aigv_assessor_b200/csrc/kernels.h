@@ -14,7 +14,7 @@ struct GemmEpilogue {
     int out_f32 = 0;                  // output element type of the C tensor map: fp32 (1) or bf16 (0)
     int accumulate = 0;               // fp32 only: C += result (TMA reduce-add; the in-place residual stream)
     int gelu = 0;                     // exact erf GELU after bias
-    int m_fast = 0;                   // set by launch_gemm: tile order with M fastest (W much larger than L2, small A)
+    int group_m = 0;                  // set by launch_gemm: tile order (0: N fastest; G: M fastest inside groups of G row tiles)
     int relu = 0;                     // ReLU after bias (plain epilogues only)
     int swiglu = 0;                   // bf16 only: W interleaves (gate, up) rows; C[M, N/2] = silu(acc[2i]) * acc[2i+1]
     // LayerNorm fusion, consumer side: A was the un-normalised activation (bf16) and W carries gamma;

@@ -39,6 +39,21 @@ def test_gemm_bias_bf16(M, N, K):
     assert emax(y.float().cpu().numpy(), ref.cpu().numpy()) < 6e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(2108, 6400, 4096), (5400, 6656, 4096), (8432, 6400, 4096)])
+def test_gemm_tile_orders_with_a_large_weight(M, N, K):
+    """W beyond 48 MB and A smaller than W selects the M-fastest tile order (<= 20 row tiles) or M fastest inside groups of
+    16 row tiles (more; the last group is ragged: 22 = 16 + 6, 33 = 16 + 16 + 1): every output tile must still be written once."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn((N, K), device="cuda", generator=g) * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    y = gemm(a, w, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    err = float((y.float() - ref).abs().max() / ref.abs().max())
+    assert err < 6e-3
+
+
 def test_gemm_gelu_bf16():
     M, N, K = 2050, 4096, 1024
     a, w = _rand((M, K), 4), _rand((N, K), 5, K ** -0.5)
