@@ -66,25 +66,51 @@ def encode_clips_sharded(engine, clips: Sequence[torch.Tensor], pool: bool = Fal
     return gather_clip_results(local, len(clips), rank, world)
 
 
-def score_clips_sharded(scorer, clips, input_ids, mos=None, motion_features=None) -> dict:
+def score_clips_sharded(scorer, clips, input_ids, mos=None, motion_features=None, clips_per_forward: int = 4) -> dict:
     """The sharded counterpart of the stage-2 eval loop (stage2_eval.py:915-975: one forward per video, score1 collected,
     SRCC / PLCC / KRCC printed at the end): every rank scores its round-robin share of ``clips`` with ``scorer``
     (scoring.ClipScorer), the scores are all-gathered once, and -- when ``mos`` is given -- the reference's metrics are computed.
 
     clips: list of pixel_values [frames, 3, 448, 448] (or uint8 frames [frames, H, W, 3]); input_ids: one [1, N] prompt for all
-    clips or a list of them; motion_features: optional list of [1, 2304] (else the scorer's own trunk runs)."""
+    clips or a list of them; motion_features: optional list of [1, 2304] (else the scorer's own trunk runs).
+    clips_per_forward: consecutive clips of a rank with the same frame count and prompt length go through ONE forward (the
+    prefill pads every call to whole 256-row tiles: 2108 tokens alone waste 8.5 % of it, four prompts together 0.2 %; measured
+    29.4 against 26.7 clips/s with InternLM2-7B). Per-clip results do not depend on the grouping beyond bf16 rounding order."""
     from . import metrics
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     mine = shard_indices(len(clips), rank, world)
-    local = []
-    for i in mine:
+
+    def prep(i):
         ids = input_ids[i] if isinstance(input_ids, (list, tuple)) else input_ids
-        mf = None if motion_features is None else motion_features[i]
         clip = clips[i]
         if clip.dtype == torch.uint8:
             clip, _ = scorer.vision.preprocess_frames(clip, max_num=1)
-        local.append(scorer(clip, ids, mf)["score1"].reshape(1).float())
+        mf = None if motion_features is None else motion_features[i]
+        return clip, ids.reshape(1, -1), mf
+
+    local, group = [], []
+
+    def flush():
+        if not group:
+            return
+        pv = torch.cat([g[0] for g in group]) if len(group) > 1 else group[0][0]
+        ids = torch.cat([g[1] for g in group]) if len(group) > 1 else group[0][1]
+        mf = None if group[0][2] is None else torch.cat([g[2].reshape(1, -1) for g in group])
+        local.append(scorer(pv, ids, mf)["score1"].reshape(-1).float())
+        group.clear()
+
+    cap = max(1, int(clips_per_forward))
+    for i in mine:
+        item = prep(i)
+        if group and (item[0].shape != group[0][0].shape or item[1].shape != group[0][1].shape
+                      or (len(group) + 1) * item[0].shape[0] > scorer.vision.max_tiles
+                      or (len(group) + 1) * item[1].shape[1] > scorer.language.max_tokens):
+            flush()
+        group.append(item)
+        if len(group) >= cap:
+            flush()
+    flush()
     local_t = torch.cat(local) if local else torch.empty((0,), dtype=torch.float32, device=scorer.device)
     scores = gather_clip_results(local_t, len(clips), rank, world)
     out = {"scores": scores}

@@ -304,7 +304,7 @@ def test_sharded_eval_loop_scores_and_metrics(golden_dir):
     sd = dict(synth.make_weights(cfg, seed=meta["seeds"]["vis"]))
     sd.update(sd_head)
     ids = torch.from_numpy(synth.make_clip_prompt(meta["n_frames"], seed=meta["seeds"]["ids"], vocab_size=meta["llm"]["vocab_size"])).cuda()
-    scorer = ClipScorer(sd, cfg, meta["llm"], synth.IMG_CONTEXT_ID, max_tiles=8, max_tokens=ids.shape[1])
+    scorer = ClipScorer(sd, cfg, meta["llm"], synth.IMG_CONTEXT_ID, max_tiles=8, max_tokens=3 * ids.shape[1])
     clips, feats = [], []
     for k in range(4):
         pv = synth.make_pixel_values(meta["n_frames"], cfg, seed=meta["seeds"]["x"] + 100 * k)
@@ -312,6 +312,11 @@ def test_sharded_eval_loop_scores_and_metrics(golden_dir):
         feats.append(ho.fake_slowfast(torch.from_numpy(pv), 1).cuda())
     res = sharding.score_clips_sharded(scorer, clips, ids, mos=[3.0, 2.0, 4.0, 1.0], motion_features=feats)
     torch.cuda.synchronize()
+    # grouped forwards (3 clips: the workspace holds 3 prompts, then 1) against one clip per forward
+    one = sharding.score_clips_sharded(scorer, clips, ids, motion_features=feats, clips_per_forward=1)
+    torch.cuda.synchronize()
+    assert float((res["scores"] - one["scores"]).abs().max()) <= 5e-3
+    assert abs(float(one["scores"][0]) - float(g["score1"][0])) <= 0.02
     assert res["scores"].shape == (4,) and torch.isfinite(res["scores"]).all()
     assert abs(float(res["scores"][0]) - float(g["score1"][0])) <= 0.02
     assert all(-1.0 <= res[k] <= 1.0 for k in ("srcc", "plcc", "krcc"))
