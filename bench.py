@@ -552,6 +552,40 @@ def run_native(args, rank, local_rank, world, out):
             lm.close()
             del lm, x7
             torch.cuda.empty_cache()
+            # BASELINE configs[1]: InternVL2-2B stage-1 eval forward (InternViT-300M + projector -> InternLM2-1.8B prefill ->
+            # quality-level logits of the answer span), one 8-frame clip at a time, frames on the host -> token ids on the host
+            try:
+                from aigv_assessor_b200 import llm_glue
+                c2, lm2 = tbl.build("1_8b", n_tok)
+                eng2 = VisionEngine(cfg, max_tiles=8, device=dev).load_state_dict(sd)     # the bench's InternVL2-2B vision path
+                tok2 = (torch.randn((c2["vocab_size"], c2["hidden_size"]), device=dev) * 0.5).to(torch.bfloat16)
+                mot2 = (torch.randn((1, c2["hidden_size"]), device=dev) * 0.5).to(torch.bfloat16)   # the motion token (resident)
+                ids2 = torch.from_numpy(synth.make_clip_prompt(8, seed=1, vocab_size=c2["vocab_size"])).to(dev)
+                clip2_host = torch.randint(0, 256, (8, fh, fw, 3), dtype=torch.uint8).pin_memory()
+                N2 = ids2.shape[1]
+                rows2 = list(range(N2 - 49, N2 - 1))
+
+                def clip_to_logits():
+                    fr = clip2_host.to(dev, non_blocking=True)
+                    pv8, _ = eng2.preprocess_frames(fr, max_num=1)
+                    x = llm_glue.splice_tokens(ids2, tok2, eng2.extract_feature(pv8), mot2, synth.IMG_CONTEXT_ID, check=False)
+                    lm2.prefill(x)
+                    return torch.argmax(lm2.logits_rows(rows2), dim=1).cpu()
+                for _ in range(2):
+                    a2 = clip_to_logits()
+                ms_l = timed(clip_to_logits, 5)
+                extra["config1_stage1_clip_to_logits_1_8b"] = {
+                    "clips_per_s": world / ms_l * 1e3, "ms_per_clip": ms_l, "frames_per_clip": 8, "tokens": int(N2),
+                    "answer_ids": int(a2.numel()), "h2d_bytes_per_clip": int(clip2_host.numel()), "d2h_bytes_per_clip": 8 * int(a2.numel()),
+                    "note": "BASELINE configs[1] shape: one 8-frame 1280x720 uint8 clip on the host -> H2D -> front end -> InternViT-300M + "
+                            "projector (2048 wide) -> splice -> InternLM2-1.8B prefill (24L, 2048, 16/8 heads of 128) -> output head on the 48 "
+                            "answer rows -> argmax -> token ids on the host; synchronous per clip"}
+                lm2.close()
+                eng2.close()
+                del lm2, eng2, tok2
+                torch.cuda.empty_cache()
+            except Exception as e:
+                extra["config1_stage1_clip_to_logits_1_8b"] = {"unavailable": repr(e)[:300]}
         except Exception as e:  # a side measurement must never take the bench line down
             extra["next1_llm_prefill_7b"] = {"unavailable": repr(e)[:300]}
 
