@@ -278,6 +278,8 @@ attention_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();               // qkv (the previous kernel's output) is complete from here on; the set-up above overlapped its tail
+    pdl_launch_dependents();
 
     if (warp >= SOFTMAX_WARPS) {
         reg_dec<G::REGS_SERVICE>();
@@ -855,9 +857,8 @@ cudaError_t launch_attention2_hd(const CUtensorMap& tm_q, const CUtensorMap& tm_
     int rot_div = grid / n_chunks;
     if (rot_div < 1) rot_div = 1;
     const float scale_log2 = softmax_scale * 1.4426950408889634f;
-    kernel<<<grid, G::THREADS, G::SMEM_BYTES, stream>>>(
-        tm_q, tm_kv, qkv, out, S, heads, static_cast<int>(n_items), n_chunks, rot_div, side_mode, scale_log2, lay);
-    return cudaGetLastError();
+    return launch_pdl(kernel, dim3(grid), dim3(G::THREADS), G::SMEM_BYTES, stream, tm_q, tm_kv, qkv, out, S, heads,
+                      static_cast<int>(n_items), n_chunks, rot_div, side_mode, scale_log2, lay);
 }
 
 __global__ void exp2_poly_test_kernel(const float* __restrict__ x, float* __restrict__ y, int n) {

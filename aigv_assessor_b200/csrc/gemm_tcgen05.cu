@@ -187,6 +187,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                           // recognises the CTA barrier and otherwise reports the slot read below as a hazard)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the previous kernel's tail (launch_pdl); its outputs -- this kernel's A, the residual
+    // stream, the row statistics -- are complete from here on
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == EPI_WARPS) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -606,8 +610,7 @@ cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     static const int group_big = [] { const char* e = getenv("AIGV_GEMM_GROUP_M"); return e ? atoi(e) : 16; }();
     epk.group_m = 0;
     if (w_bytes > 48e6 && a_bytes < w_bytes) epk.group_m = (num_m <= 20 || group_big <= 0) ? num_m : group_big;
-    kern<<<2 * pairs, C::THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmX, M, N, K, epk);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmC, tmX, M, N, K, epk);
 }
 
 }  // namespace

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace aigv {
 
@@ -105,6 +106,24 @@ inline cudaError_t ensure_smem_optin(const void* kernel, int bytes, unsigned lon
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess && dev >= 0 && dev < 64) mask |= 1ull << dev;
     return e;
+}
+
+// Launch `kernel` with programmatic stream serialization (PDL): its prologue may overlap the tail of the previous kernel of the
+// stream. ONLY for kernels that execute pdl_wait() (ptx.cuh) before their first global-memory access. AIGV_PDL=0 turns it off.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static const int enabled = [] { const char* e = getenv("AIGV_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = enabled;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- row-wise / bandwidth kernels --------------------------------------------------------------------------------

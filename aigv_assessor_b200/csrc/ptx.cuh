@@ -139,6 +139,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
+// Programmatic dependent launch (kernels.h: launch_pdl): a kernel launched that way may become resident while its predecessor in
+// the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps that
+// tail, nothing after it runs before the predecessor's memory is complete and visible. A no-op for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+// Lets the NEXT kernel of the stream be scheduled as soon as SMs free up (it still waits in its own pdl_wait()).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 
