@@ -636,7 +636,11 @@ def run_native(args, rank, local_rank, world, out):
                        "one all-gather of the visual tokens at the end of the timed region)",
                        "l2": f"{R} rotating input batches; ~{eng.lib.aigv_workspace_bytes(eng._h, eng.max_tiles) / 2**30:.1f} GiB "
                              "activation working set per step >> 126 MB L2",
-                       "gflop_per_frame": cfg.flops_per_frame() / 1e9},
+                       "gflop_per_frame": cfg.flops_per_frame() / 1e9,
+                       "timed_region": "every launch of the timed steps is bracketed by CUDA events on the launching stream (the "
+                                       "roofline's per-kernel times); the events cost ~1% of the step (profiles/r2z_pdl_ab.txt: 46.9 ms "
+                                       "with them, 46.4 without) and keep programmatic dependent launch from overlapping kernel "
+                                       "prologues there; the e2e leg runs without them"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e / args.steps,
