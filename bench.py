@@ -638,8 +638,8 @@ def run_native(args, rank, local_rank, world, out):
                              "activation working set per step >> 126 MB L2",
                        "gflop_per_frame": cfg.flops_per_frame() / 1e9,
                        "timed_region": "every launch of the timed steps is bracketed by CUDA events on the launching stream (the "
-                                       "roofline's per-kernel times); the events cost ~1% of the step (profiles/r2z_pdl_ab.txt: 46.9 ms "
-                                       "with them, 46.4 without) and keep programmatic dependent launch from overlapping kernel "
+                                       "roofline's per-kernel times); the events cost ~1% of the step (profiles/r2z_pdl_ab.txt: 46.7 ms "
+                                       "with them, 46.3 without) and keep programmatic dependent launch from overlapping kernel "
                                        "prologues there; the e2e leg runs without them"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
