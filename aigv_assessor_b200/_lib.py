@@ -129,6 +129,7 @@ SIGNATURES = {
     "aigv_assemble_tokens_stats": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "aigv_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "aigv_exp2_poly": (C.c_int, [_P, _P, C.c_int, _P]),
+    "aigv_gemm_tile_order": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
     "aigv_splice_tokens": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
     "aigv_mlpscore": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_int, _P]),
     "aigv_llm_create": (C.c_int, [C.POINTER(LlmCfg), C.POINTER(_P)]),

@@ -951,6 +951,22 @@ int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int 
     return AIGV_OK;
 }
 
+int aigv_gemm_tile_order(int M, int N, int K, int* group_m, int32_t* m_blk, int32_t* n_blk, int capacity) {
+    if (M <= 0 || N <= 0 || K <= 0 || !group_m) return AIGV_ERR_INVALID;
+    const int num_m = (M + 255) / 256, num_n = (N + 255) / 256;
+    *group_m = gemm_group_m(M, N, K);
+    if (m_blk && n_blk) {
+        if (capacity < num_m * num_n) return AIGV_ERR_INVALID;
+        for (int t = 0; t < num_m * num_n; ++t) {
+            int mb, nb;
+            tile_coords(t, num_m, num_n, *group_m, mb, nb);
+            m_blk[t] = mb;
+            n_blk[t] = nb;
+        }
+    }
+    return AIGV_OK;
+}
+
 int aigv_exp2_poly(const float* x, float* y, int n, void* stream) {
     if (!x || !y || n <= 0) return AIGV_ERR_INVALID;
     AIGV_TRY0(launch_exp2_poly_test(x, y, n, static_cast<cudaStream_t>(stream)));

@@ -67,24 +67,6 @@ struct Cfg {
 // LN fusion: the A operand was the un-normalised activation x (bf16) and W carries gamma, so
 //   LN(x) W^T = rstd * (x W'^T - mean * wsum) + (b + W beta),   wsum[n] = sum_k W'[n,k]
 // with the row's mean / rstd taken from the (sum, sum of squares) the producing GEMM accumulated.
-// Output tile -> (row tile, column tile). group_m = 0: N fastest (a wave shares few A row tiles and the whole, L2-resident W);
-// group_m = G > 0: M fastest inside groups of G row tiles, the groups walked over all of N one after the other (G >= num_m: plain
-// M fastest -- every W tile leaves DRAM once while a small A stays in L2).
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
-    if (group_m <= 0) {
-        m_blk = tile / num_n;
-        n_blk = tile - m_blk * num_n;
-        return;
-    }
-    const int per_group = group_m * num_n;
-    const int g = tile / per_group;
-    const int first_m = g * group_m;
-    const int gsz = min(num_m - first_m, group_m);
-    const int in_g = tile - g * per_group;
-    n_blk = in_g / gsz;
-    m_blk = first_m + (in_g - n_blk * gsz);
-}
-
 template <int kAct>   // 0: none, 1: erf GELU, 2: SwiGLU on (gate, up) column pairs (applied by the caller: halves the width)
 __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep, float mean, float rstd) {
     if (ep.ln_stats) {
@@ -605,15 +587,19 @@ cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     // (measured on the 7B w1|w3 GEMM, M = 2108: 2.12 GB of DRAM reads per launch with N fastest against 0.25 GB algorithmic).
     // With many row tiles (several prompts per prefill: A no longer sits in L2 next to the W stream) M goes fastest inside
     // groups of 16 row tiles (7B w1|w3 at four prompts per prefill: 26.6 against 28.0 ms per prompt; 8: 27.3, 4: 27.8).
-    const double w_bytes = 2.0 * N * K, a_bytes = 2.0 * M * K;
-    const int num_m = (M + 2 * BM - 1) / (2 * BM);
-    static const int group_big = [] { const char* e = getenv("AIGV_GEMM_GROUP_M"); return e ? atoi(e) : 16; }();
-    epk.group_m = 0;
-    if (w_bytes > 48e6 && a_bytes < w_bytes) epk.group_m = (num_m <= 20 || group_big <= 0) ? num_m : group_big;
+    epk.group_m = gemm_group_m(M, N, K);
     return launch_pdl(kern, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, stream, tmA, tmB, tmC, tmX, M, N, K, epk);
 }
 
 }  // namespace
+
+int gemm_group_m(int M, int N, int K) {
+    const double w_bytes = 2.0 * N * K, a_bytes = 2.0 * M * K;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
+    static const int group_big = [] { const char* e = getenv("AIGV_GEMM_GROUP_M"); return e ? atoi(e) : 16; }();
+    if (w_bytes > 48e6 && a_bytes < w_bytes) return (num_m <= 20 || group_big <= 0) ? num_m : group_big;
+    return 0;
+}
 
 int gemm_box_rows_a() { return BM; }
 int gemm_box_rows_b() { return BNH; }

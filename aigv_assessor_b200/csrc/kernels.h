@@ -108,6 +108,27 @@ inline cudaError_t ensure_smem_optin(const void* kernel, int bytes, unsigned lon
     return e;
 }
 
+// Output tile -> (row tile, column tile). group_m = 0: N fastest (a wave shares few A row tiles and the whole, L2-resident W);
+// group_m = G > 0: M fastest inside groups of G row tiles, the groups walked over all of N one after the other (G >= num_m: plain
+// M fastest -- every W tile leaves DRAM once while a small A stays in L2).
+__host__ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+    if (group_m <= 0) {
+        m_blk = tile / num_n;
+        n_blk = tile - m_blk * num_n;
+        return;
+    }
+    const int per_group = group_m * num_n;
+    const int g = tile / per_group;
+    const int first_m = g * group_m;
+    const int gsz = num_m - first_m < group_m ? num_m - first_m : group_m;
+    const int in_g = tile - g * per_group;
+    n_blk = in_g / gsz;
+    m_blk = first_m + (in_g - n_blk * gsz);
+}
+
+// The tile order launch_gemm picks for an [M, K] x [N, K]^T product (0: N fastest, G: groups of G row tiles, >= row tiles: M fastest).
+int gemm_group_m(int M, int N, int K);
+
 // Launch `kernel` with programmatic stream serialization (PDL): its prologue may overlap the tail of the previous kernel of the
 // stream. ONLY for kernels that execute pdl_wait() (ptx.cuh) before their first global-memory access. AIGV_PDL=0 turns it off.
 template <typename... KArgs, typename... Args>

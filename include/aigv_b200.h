@@ -131,6 +131,10 @@ int aigv_assemble_tokens_stats(const float* pe, const float* cls, const float* p
  * (flash_attention.py:52-55 / modeling_intern_vit.py:143-157). Any sequence length; head_dim 64 or 128. */
 int aigv_attention(const void* qkv_bf16, void* out_bf16, int frames, int S, int heads, int head_dim, float scale,
                    void* stream);
+/* Test hook (host only, no GPU work): the order in which the persistent GEMM walks the 256 x 256 output tiles of an [M, K] x [N, K]^T
+ * product. *group_m: 0 = N fastest, G = M fastest inside groups of G row tiles (>= the number of row tiles: plain M fastest). With
+ * m_blk / n_blk (capacity >= tiles): the (row tile, column tile) of tile 0, 1, ... exactly as the kernel computes them. */
+int aigv_gemm_tile_order(int M, int N, int K, int* group_m, int32_t* m_blk, int32_t* n_blk, int capacity);
 /* Test hook: y[i] = 2^x[i] exactly as the attention kernel evaluates the share of its exponentials that runs on the
  * FMA pipe instead of MUFU (Cody-Waite split + cubic; x fp32 [n], device pointers). */
 int aigv_exp2_poly(const float* x, float* y, int n, void* stream);

@@ -337,3 +337,51 @@ def test_slowfast_restatement_reproduces_the_published_flops():
         if s < 3:
             macs += 2 * sf.FAST["out"][s] * sf.FAST["out"][s] * 7 * Ts * cur * cur
     assert round((macs + 2304 * 400) / 1e9, 2) == 65.71
+
+
+def test_gemm_tile_order_is_a_bijection_for_every_regime():
+    """aigv_gemm_tile_order (host only): the persistent GEMM's tile walk -- N fastest, M fastest, M fastest inside groups of 16 row
+    tiles with a ragged last group -- must visit every (row tile, column tile) exactly once, and consecutive tiles of a group must
+    share their column tile (that is what keeps the weight stream single-pass)."""
+    import ctypes as C
+    import numpy as np
+    from aigv_assessor_b200 import _lib
+    lib = _lib.load()
+    cases = {  # (M, N, K): expected regime
+        (65600, 4096, 1024): "n_fast",      # the ViT's fc1: small, L2-resident W
+        (2108, 28672, 4096): "m_fast",      # 7B w1|w3, one prompt: 9 row tiles
+        (8432, 28672, 4096): "grouped",     # four prompts: 33 row tiles = 16 + 16 + 1
+        (5400, 28672, 4096): "grouped",     # 22 = 16 + 6
+        (8432, 4096, 14336): "n_fast",      # 7B w2: A larger than W
+    }
+    for (M, N, K), regime in cases.items():
+        num_m, num_n = (M + 255) // 256, (N + 255) // 256
+        g = C.c_int(-1)
+        mb = np.empty(num_m * num_n, dtype=np.int32)
+        nb = np.empty(num_m * num_n, dtype=np.int32)
+        st = lib.aigv_gemm_tile_order(M, N, K, C.byref(g), mb.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      nb.ctypes.data_as(C.POINTER(C.c_int32)), mb.size)
+        assert st == 0
+        if regime == "n_fast":
+            assert g.value == 0
+        elif regime == "m_fast":
+            assert g.value >= num_m
+        else:
+            assert 0 < g.value < num_m
+        assert ((0 <= mb) & (mb < num_m) & (0 <= nb) & (nb < num_n)).all()
+        assert len(set(zip(mb.tolist(), nb.tolist()))) == num_m * num_n, (M, N, K)
+        if regime == "n_fast":
+            assert (nb[:num_n] == np.arange(num_n)).all() and (mb[:num_n] == 0).all()
+        if regime == "m_fast":
+            assert (mb[:num_m] == np.arange(num_m)).all() and (nb[:num_m] == 0).all()
+        if regime == "grouped":
+            G = g.value
+            assert (mb[:G] == np.arange(G)).all() and (nb[:G] == 0).all()          # first group, first column tile
+            last = num_m - (num_m // G) * G or G
+            tail = mb[-last * num_n:]
+            assert tail.min() == num_m - last and tail.max() == num_m - 1           # the ragged last group closes the walk
+    # too small a buffer is refused
+    g = C.c_int(0)
+    small = np.empty(4, dtype=np.int32)
+    assert lib.aigv_gemm_tile_order(8432, 28672, 4096, C.byref(g), small.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    small.ctypes.data_as(C.POINTER(C.c_int32)), 4) != 0
