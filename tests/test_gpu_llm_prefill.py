@@ -320,3 +320,41 @@ def test_sharded_eval_loop_scores_and_metrics(golden_dir):
     assert res["scores"].shape == (4,) and torch.isfinite(res["scores"]).all()
     assert abs(float(res["scores"][0]) - float(g["score1"][0])) <= 0.02
     assert all(-1.0 <= res[k] <= 1.0 for k in ("srcc", "plcc", "krcc"))
+
+
+def test_prefill_full_width_batch_equals_single_prompt():
+    """InternLM2-7B's widths (4096, 32/8 heads of 128, I = 14336; two layers) on four copies of one 2108-token clip prompt: 33 row tiles
+    select the grouped GEMM tile order for w1|w3 (M fastest inside groups of 16 row tiles) where a single prompt runs plain M fastest.
+    Tile order, work-list dealing and batch position must not change a single bit of a row: the residual stream of every copy equals
+    the single-prompt prefill exactly (a size-independent property, checked at the real size)."""
+    llm = dict(hidden_size=4096, num_hidden_layers=2, num_attention_heads=32, num_key_value_heads=8, intermediate_size=14336,
+               vocab_size=128, rms_norm_eps=1e-5, rope_theta=1e6, max_position_embeddings=32768)
+    B, N, H = 4, 2108, 4096
+    eng = L.LanguageEngine(llm, max_tokens=B * N)
+    g = torch.Generator(device="cuda").manual_seed(7)
+
+    def rnd(shape, fan_in):
+        return ((torch.rand(shape, device="cuda", generator=g) * 2 - 1) * fan_in ** -0.5).to(torch.bfloat16)
+    for i in range(2):
+        p = f"model.layers.{i}."
+        eng.set_weight(p + "attention.wqkv.weight", rnd((6144, H), H / 4.0))
+        eng.set_weight(p + "attention.wo.weight", rnd((H, H), H))
+        eng.set_weight(p + "feed_forward.w1.weight", rnd((14336, H), H))
+        eng.set_weight(p + "feed_forward.w3.weight", rnd((14336, H), H))
+        eng.set_weight(p + "feed_forward.w2.weight", rnd((H, 14336), 14336))
+        eng.set_weight(p + "attention_norm.weight", torch.ones(H, device="cuda"))
+        eng.set_weight(p + "ffn_norm.weight", torch.ones(H, device="cuda"))
+    eng.set_weight("model.norm.weight", torch.ones(H, device="cuda"))
+    eng.set_weight("output.weight", rnd((128, H), H))
+    eng._check(eng.lib.aigv_llm_finalize_weights(eng._h, None), "finalize")
+    eng._finalized = True
+    one = (torch.randn((1, N, H), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    eng.prefill(one)
+    x1 = eng.residual().clone()
+    eng.prefill(one.repeat(B, 1, 1).contiguous())
+    xb = eng.residual()
+    torch.cuda.synchronize()
+    assert torch.isfinite(x1).all() and float(x1.abs().max()) > 0.1
+    for b in range(B):
+        assert torch.equal(xb[b], x1[0]), f"copy {b} of the prompt differs from the single-prompt prefill"
+    eng.close()
