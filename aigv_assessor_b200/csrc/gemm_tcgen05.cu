@@ -67,7 +67,7 @@ struct Cfg {
 // LN fusion: the A operand was the un-normalised activation x (bf16) and W carries gamma, so
 //   LN(x) W^T = rstd * (x W'^T - mean * wsum) + (b + W beta),   wsum[n] = sum_k W'[n,k]
 // with the row's mean / rstd taken from the (sum, sum of squares) the producing GEMM accumulated.
-template <int kAct>   // 0: none, 1: erf GELU, 2: SwiGLU on (gate, up) column pairs (applied by the caller: halves the width)
+template <int kAct>   // 0: none, 1: erf GELU, 2: SwiGLU on (gate, up) column pairs (applied by the caller: halves the width), 3: rotary (by the caller)
 __device__ __forceinline__ void epilogue_math(float (&x)[32], int col0, const GemmEpilogue& ep, float mean, float rstd) {
     if (ep.ln_stats) {
         // x = rstd * (acc - mean * wsum) + bias as two FMAs per element: fma(rstd, acc, fma(-mean*rstd, wsum, bias))
@@ -540,6 +540,40 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     flush(packed, (colb + c) >> 1);
                 }
+            } else if (kAct == 3) {
+                // Rotary embedding (InternLM2 wqkv, 128-wide heads): this warp's 128-column slice is one head slot of a kv
+                // group. Chunk pairs (0, 64) and (32, 96) hold (x[j], x[j + 64]): rotate in fp32, round once.
+                static_assert(kAct != 3 || SLICE_COLS == 128, "rotary epilogue: one 128-wide head per slice");
+                const bool rot = (colb % ep.rope_group_cols) < ep.rope_group_cols - 128;   // not the group's value head
+                const int row = row0 + lane;
+                const float4* cs = reinterpret_cast<const float4*>(ep.rope_tab + static_cast<size_t>(row < M ? row % ep.rope_N : 0) * 64);
+                uint4 lo[8], hi[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float xa[32], xc[32];
+                    load32(32 * h, xa);
+                    load32(32 * h + 64, xc);
+                    if (rot) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float4 t = __ldg(cs + ((32 * h + j) >> 1));   // (cos, sin) of j and j + 1
+                            const float a0 = xa[j], a1 = xa[j + 1], b0 = xc[j], b1 = xc[j + 1];
+                            xa[j] = a0 * t.x - b0 * t.y;
+                            xc[j] = b0 * t.x + a0 * t.y;
+                            xa[j + 1] = a1 * t.z - b1 * t.w;
+                            xc[j + 1] = b1 * t.z + a1 * t.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        lo[4 * h + j] = make_uint4(pack_bf16x2(xa[8 * j], xa[8 * j + 1]), pack_bf16x2(xa[8 * j + 2], xa[8 * j + 3]),
+                                                   pack_bf16x2(xa[8 * j + 4], xa[8 * j + 5]), pack_bf16x2(xa[8 * j + 6], xa[8 * j + 7]));
+                        hi[4 * h + j] = make_uint4(pack_bf16x2(xc[8 * j], xc[8 * j + 1]), pack_bf16x2(xc[8 * j + 2], xc[8 * j + 3]),
+                                                   pack_bf16x2(xc[8 * j + 4], xc[8 * j + 5]), pack_bf16x2(xc[8 * j + 6], xc[8 * j + 7]));
+                    }
+                }
+                flush(lo, colb);
+                flush(hi, colb + 64);
             } else {
 #pragma unroll 1
                 for (int c = 0; c < SLICE_COLS; c += 64) {  // 64-column bf16 staging tiles (128 B rows)
@@ -641,6 +675,12 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                           : launch_variant<1, false, AIGV_GELU_WARPS, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
     }
     if (ep.out_f32) return launch_variant<0, true, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    if (ep.rope_tab) {
+        if (ep.rope_N <= 0 || ep.rope_group_cols < 256 || (ep.rope_group_cols % 128) != 0 || (N % ep.rope_group_cols) != 0 || ep.colscale ||
+            ep.relu)
+            return cudaErrorInvalidValue;
+        return launch_variant<3, false, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
+    }
     return launch_variant<0, false, 8, 0>(tmA, tmB, tmC, tmC, M, N, K, ep, num_sms, stream);
 }
 

@@ -37,6 +37,12 @@ struct GemmEpilogue {
     // that value; delta_in = a pending d (bf16 [M, N]) that this (fp32, long-K) producer adds on top of x_old.
     int delta_out = 0;
     const __nv_bfloat16* delta_in = nullptr;
+    // Rotary embedding in the epilogue (bf16 output, 128-wide heads; InternLM2's wqkv): the columns are groups of rope_group_cols =
+    // (G + 2) * 128 -- G query heads, one key head, one value head -- and every 128-column slot but the last of a group is rotated
+    // in the rotate-half form with (cos, sin) = rope_tab[(row % rope_N) * 64 + j] (modeling_internlm2.py:247-260), in fp32 on the
+    // accumulator, before the single rounding to bf16.
+    const float2* rope_tab = nullptr;
+    int rope_N = 0, rope_group_cols = 0;
 };
 
 // ---- TMA descriptors (host) -------------------------------------------------------------------------------------

@@ -218,6 +218,7 @@ struct aigv_llm_handle {
     // activation maps, rebuilt when the token count changes
     int maps_m = -1;
     CUtensorMap a_xb, a_attn, a_hm, q_map, kv_map, c_x, c_xb, c_qkv, c_h13, c_hm;
+    bool fused_rope = true;     // AIGV_LLM_UNFUSED_ROPE=1: wqkv GEMM, then the standalone rotary kernel (A/B runs; always for heads != 128)
     bool fused_swiglu = true;   // AIGV_LLM_UNFUSED_SWIGLU=1: w1|w3 GEMM -> h13, then the standalone SwiGLU kernel (A/B runs)
 };
 
@@ -313,6 +314,8 @@ int aigv_llm_create(const aigv_llm_cfg* cfg, aigv_llm_handle** out) {
     {
         const char* e = getenv("AIGV_LLM_UNFUSED_SWIGLU");
         h->fused_swiglu = !(e && e[0] == '1') && (h->I % 64) == 0;
+        const char* er = getenv("AIGV_LLM_UNFUSED_ROPE");
+        h->fused_rope = !(er && er[0] == '1') && h->hd == 128;
     }
     const size_t M = h->Mx;
     bool ok = lalloc(h, &h->x, M * h->H) && lalloc(h, &h->xb, M * h->H) && lalloc(h, &h->qkv, M * h->QW) &&
@@ -482,8 +485,12 @@ int aigv_llm_prefill(aigv_llm_handle* h, const void* inputs_embeds_bf16, int B, 
         cons.ln_stats = h->stats; cons.ln_nparts = h->parts; cons.ln_wsum = nullptr; cons.ln_inv_d = 1.0f / (float)H; cons.ln_eps = h->cfg.rms_norm_eps;
         GemmEpilogue prod;   // fused-residual producer: x += acc; xb = bf16(x); stats
         prod.out_f32 = 1; prod.fused_residual = 1; prod.resid_in = h->x; prod.stats_out = h->stats;
-        LLM_LAUNCH(launch_gemm(h->a_xb, w.tm_wqkv, h->c_qkv, M, h->QW, H, cons, h->num_sms, st), "wqkv");
-        {
+        if (h->fused_rope) {   // rotary embedding of the q / k heads in the wqkv epilogue (fp32 accumulator, one rounding)
+            GemmEpilogue qk = cons;
+            qk.rope_tab = h->rope; qk.rope_N = N; qk.rope_group_cols = (h->G + 2) * h->hd;
+            LLM_LAUNCH(launch_gemm(h->a_xb, w.tm_wqkv, h->c_qkv, M, h->QW, H, qk, h->num_sms, st), "wqkv + rope");
+        } else {
+            LLM_LAUNCH(launch_gemm(h->a_xb, w.tm_wqkv, h->c_qkv, M, h->QW, H, cons, h->num_sms, st), "wqkv");
             const long long n = (long long)M * h->nkv * (h->G + 1) * (half / 8);
             LLM_LAUNCH((llm_rope_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->qkv, h->rope, M, N, h->QW, h->nkv, h->G, h->hd), cudaGetLastError()), "rope");
         }

@@ -477,9 +477,9 @@ def run_native(args, rank, local_rank, world, out):
             extra["next1_llm_prefill_7b"] = {
                 "prompts_per_s": world / ms7 * 1e3, "ms_per_prompt": ms7, "tokens": n_tok, "tflops_per_gpu": fl7 / ms7 / 1e9,
                 "frac_of_sustained_peak": fl7 / ms7 / 1e9 / measured_peaks()["sustained"], "tflop_per_prompt": fl7 / 1e12,
-                "finite": bool(torch.isfinite(lg).all()), "launches_per_prompt": 1 + 6 * c7["num_hidden_layers"] + 3,
+                "finite": bool(torch.isfinite(lg).all()), "launches_per_prompt": 1 + 5 * c7["num_hidden_layers"] + 3,
                 "note": "InternLM2-7B decoder stack (32L, 4096, 32/8 heads of 128, I=14336) on the spliced prompt of one 8-frame "
-                        "clip: RMSNorm-fused wqkv, rotary, causal GQA tcgen05 attention, wo + residual, w1|w3 + SwiGLU epilogue, w2 + "
+                        "clip: RMSNorm-fused wqkv with the rotary embedding in its epilogue, causal GQA tcgen05 attention, wo + residual, w1|w3 + SwiGLU epilogue, w2 + "
                         "residual; final norm + output head on row -4 and the 48 answer rows only; random-init weights on the device"}
             if world == 1 and not args.no_ref_gpu:
                 try:

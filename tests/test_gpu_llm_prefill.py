@@ -118,7 +118,7 @@ def test_prefill_matches_the_oracle_on_random_embeddings(golden_dir):
     e_l = vo.error_metrics(logits.numpy(), ref_l.numpy())
     print(f"prefill vs oracle: hidden rows e_max/e_l2 {e_h}  logits {e_l}")
     assert e_h[0] < 2e-2 and e_l[0] < 2e-2
-    assert eng.launch_count >= 1 + 6 * llm["num_hidden_layers"]
+    assert eng.launch_count >= 1 + 5 * llm["num_hidden_layers"]   # seed + (wqkv+rope, attention, wo, w1|w3+SwiGLU, w2) per layer
 
 
 def test_score_with_everything_on_the_gpu(golden_dir):
