@@ -8,6 +8,8 @@ from tests.gpu_util import ptr, stream
 
 lib = _lib.load()
 frames, S, H, d, D, I = 64, 1025, 16, 64, 1024, 4096
+if len(sys.argv) > 3:
+    S = int(sys.argv[3])   # e.g. 1024: no class-token row (the side warps idle), no lone tail key
 M = frames * S
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
