@@ -37,7 +37,7 @@ def weight_spec(cfg: VisionPathConfig):
     """Yield (name, shape, dist) for every tensor of the path under the reference's state-dict names.
 
     dist is ("uniform", fan_in) -- U(-1/sqrt(fan_in), 1/sqrt(fan_in)), torch's Linear/Conv default -- or
-    ("normal", std, mean). make_weights() draws them in this order; GPU-side generators (tools_bench_6b.py) reuse it.
+    ("normal", std, mean). make_weights() draws them in this order; GPU-side generators (tools/bench_6b.py) reuse it.
     """
     D, I, C, W = cfg.hidden_size, cfg.intermediate_size, cfg.llm_hidden, cfg.shuffled_width
     P = cfg.patch_size

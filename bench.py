@@ -459,7 +459,8 @@ def run_native(args, rank, local_rank, world, out):
     # ---- next-1: InternLM2-7B prefill of one 8-frame clip prompt (2108 tokens), one replica per GPU ----------
     if not args.no_extra and not args.no_llm:
         try:
-            import tools_bench_llm as tbl
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_llm as tbl
             torch.cuda.empty_cache()
             n_tok = 1 + 8 * 258 + 3 + 40      # <s>, 8 x (<img> 256 x <IMG_CONTEXT> </img>), the motion slot, 40 text tokens
             c7, lm = tbl.build("7b", 4 * n_tok)   # workspace for the 4-clip step of config 3 below

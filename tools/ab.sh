@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B prebuilt library variants on ONE box (per-kernel times differ by several % between boxes).
-# Usage: bash tools_ab.sh name=path[,ENV=VAL] ... ; writes gpurun_out/ab_<name>_<rep>.json
+# Usage: bash tools/ab.sh name=path[,ENV=VAL] ... ; writes gpurun_out/ab_<name>_<rep>.json
 mkdir -p gpurun_out
 for rep in 1 2; do
   for spec in "$@"; do

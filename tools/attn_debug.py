@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """GPU box: per-(frame, head, 128-row tile) error map of aigv_attention against the fp32 softmax reference."""
+import _path  # noqa: F401  (repository root on sys.path)
 import sys
 import numpy as np
 import torch

@@ -4,8 +4,9 @@ with its projector through the same library, timed on one B200. Weights are rand
 synth.weight_spec (5.9 G parameters: numpy on the host would take minutes). This is a side measurement (it prints one
 JSON line with the same keys as bench.py's kernels table); bench.py stays the contract benchmark of the 300M workload.
 
-Usage (GPU box): python tools_bench_6b.py [--frames 16] [--layers 48] [--steps 5]
+Usage (GPU box): python tools/bench_6b.py [--frames 16] [--layers 48] [--steps 5]
 """
+import _path  # noqa: F401  (repository root on sys.path)
 import argparse
 import json
 import sys

@@ -1,5 +1,6 @@
 """GPU box: time the InternLM2 prefill (aigv_llm_prefill) on random-init weights generated on the device.
-Usage: python tools_bench_llm.py [7b|1_8b] [N] [B ...]   -> one JSON line per batch size."""
+Usage: python tools/bench_llm.py [7b|1_8b] [N] [B ...]   -> one JSON line per batch size."""
+import _path  # noqa: F401  (repository root on sys.path)
 import json
 import sys
 import time

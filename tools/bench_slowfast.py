@@ -1,4 +1,5 @@
 """GPU box: time the SlowFast-R50 motion trunk (aigv_assessor_b200/slowfast.py) per 8-frame 448x448 clip."""
+import _path  # noqa: F401  (repository root on sys.path)
 import json
 import sys
 

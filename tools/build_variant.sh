@@ -1,5 +1,5 @@
 #!/bin/bash
-# Build a library variant for same-box A/B runs: bash tools_build_variant.sh <name> [extra nvcc flags...]
+# Build a library variant for same-box A/B runs: bash tools/build_variant.sh <name> [extra nvcc flags...]
 # -> variants/lib_<name>.so (objects compiled in parallel). Select with AIGV_LIB=$PWD/variants/lib_<name>.so.
 set -e
 name=$1; shift

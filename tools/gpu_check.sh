@@ -1,6 +1,6 @@
 #!/bin/bash
 # Run every GPU test file in its own process (a trapped kernel poisons only its own CUDA context), with timeouts.
-# Usage (on the GPU box): bash tools_gpu_check.sh [extra pytest args]
+# Usage (on the GPU box): bash tools/gpu_check.sh [extra pytest args]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv | tee gpurun_out/gpu.txt
 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -2

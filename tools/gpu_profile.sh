@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu passes for profiles/: launch list of one bench step + full captures of the GEMM and attention kernels.
-# Usage (GPU box): bash tools_gpu_profile.sh <round-tag>
+# Usage (GPU box): bash tools/gpu_profile.sh <round-tag>
 tag=${1:-r1}
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extra --no-ref-gpu"

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, total, average, share."""
+import _path  # noqa: F401  (repository root on sys.path)
 import collections
 import csv
 import io

@@ -1,9 +1,9 @@
 #!/bin/bash
 # GPU box: ncu evidence for the InternLM2-7B prefill (next-1): launch list of one prefill + full captures of the causal
-# attention kernel and of the w1|w3 SwiGLU GEMM. Usage: bash tools_llm_profile.sh <tag>
+# attention kernel and of the w1|w3 SwiGLU GEMM. Usage: bash tools/llm_profile.sh <tag>
 tag=${1:-r2h}
 mkdir -p gpurun_out
-B="python tools_bench_llm.py 7b 2108 1 noref"
+B="python tools/bench_llm.py 7b 2108 1 noref"
 PATHK='regex:gemm_bf16_tn|attention_fwd2|llm_seed_residual|llm_rope_kernel|llm_silu_mul|llm_norm_rows'
 # the first prefill (196 launches incl. the rope table's neighbours) is the cold warm-up: list the second one
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$PATHK" -s 195 -c 195 --csv --log-file gpurun_out/llm_launches_${tag}.csv $B > gpurun_out/llm_launches_${tag}.log 2>&1

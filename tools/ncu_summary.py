@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Print the judged subset of an `ncu --set full` report (.ncu-rep) as text: one block per captured kernel launch.
 
-Usage: python tools_ncu_summary.py gpurun_out/prof_gemm_r1.ncu-rep > profiles/r1_ncu_gemm_summary.txt
+Usage: python tools/ncu_summary.py gpurun_out/prof_gemm_r1.ncu-rep > profiles/r1_ncu_gemm_summary.txt
 """
+import _path  # noqa: F401  (repository root on sys.path)
 import csv
 import io
 import subprocess

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """Micro-benchmarks of single ops through the C-ABI (GPU box): attention and the four layer GEMM shapes."""
+import _path  # noqa: F401  (repository root on sys.path)
 import sys
 import torch
 sys.path.insert(0, ".")

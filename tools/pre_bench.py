@@ -1,4 +1,5 @@
-"""GPU box: time aigv_preprocess_u8 alone (device-resident uint8 frames) for a few source sizes. Usage: python tools_pre_bench.py"""
+"""GPU box: time aigv_preprocess_u8 alone (device-resident uint8 frames) for a few source sizes. Usage: python tools/pre_bench.py"""
+import _path  # noqa: F401  (repository root on sys.path)
 import torch
 from aigv_assessor_b200.config import tiny
 from aigv_assessor_b200.engine import VisionEngine

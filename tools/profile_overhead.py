@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """GPU box: does the per-launch CUDA-event instrumentation (aigv_profile_*) slow the timed step? 10 steps of the bench workload with
 the instrumentation off / on, alternating."""
+import _path  # noqa: F401  (repository root on sys.path)
 import sys
 import torch
 sys.path.insert(0, ".")

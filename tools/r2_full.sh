@@ -1,12 +1,12 @@
 #!/bin/bash
 # Full GPU validation: every -m gpu test file, op-bench A/B of the variants, then the bench line.
 mkdir -p gpurun_out
-bash tools_gpu_check.sh 2>&1 | grep -E "===|passed|failed|error|Error|e_max|score1|tile 63" | tee gpurun_out/check.log
+bash tools/gpu_check.sh 2>&1 | grep -E "===|passed|failed|error|Error|e_max|score1|tile 63" | tee gpurun_out/check.log
 for rep in 1 2; do
-  echo "== default"; timeout 120 python tools_op_bench.py all 20 2>&1 | tail -5
+  echo "== default"; timeout 120 python tools/op_bench.py all 20 2>&1 | tail -5
   for v in variants/lib_*.so; do
     [ -f $v ] || continue
-    echo "== $v"; AIGV_LIB=$PWD/$v timeout 120 python tools_op_bench.py all 20 2>&1 | tail -5
+    echo "== $v"; AIGV_LIB=$PWD/$v timeout 120 python tools/op_bench.py all 20 2>&1 | tail -5
   done
 done | tee gpurun_out/op_ab.log
 timeout 900 python bench.py 2> gpurun_out/bench_err.log > gpurun_out/bench_r2a.json; tail -3 gpurun_out/bench_err.log

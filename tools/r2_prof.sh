@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 for f in tests/test_gpu_attention.py tests/test_gpu_llm_glue.py; do
   timeout -s KILL 600 python -m pytest $f -q -m gpu -s 2>&1 | grep -E "passed|failed|rror|all-CUDA" | tee -a gpurun_out/check_$tag.log
 done
-for rep in 1 2; do timeout 120 python tools_op_bench.py attn 20 2>&1 | tail -1; done | tee gpurun_out/attn_$tag.log
-bash tools_gpu_profile.sh $tag > gpurun_out/profile_$tag.log 2>&1
+for rep in 1 2; do timeout 120 python tools/op_bench.py attn 20 2>&1 | tail -1; done | tee gpurun_out/attn_$tag.log
+bash tools/gpu_profile.sh $tag > gpurun_out/profile_$tag.log 2>&1
 tail -3 gpurun_out/profile_$tag.log
 # race / memory checks on small cases (the sanitizer serialises everything: keep the shapes tiny)
 SAN=/usr/local/cuda/bin/compute-sanitizer

@@ -9,4 +9,4 @@ timeout 600 $SAN --tool racecheck --racecheck-report all python -m pytest tests/
 grep -E "RACECHECK SUMMARY|passed|failed|Error: Race" gpurun_out/racecheck_attention_$tag.txt | sort | uniq -c | head
 timeout 600 $SAN --tool memcheck python -m pytest tests/test_gpu_attention.py tests/test_gpu_llm_glue.py tests/test_gpu_gemm.py -q -m gpu -k "1-128-1-64 or 2-100-2-64 or 1-300-2-64 or splice or mlpscore_head or exact_small or residual_stats" > gpurun_out/memcheck_$tag.txt 2>&1
 grep -E "ERROR SUMMARY|passed|failed" gpurun_out/memcheck_$tag.txt | head
-for rep in 1 2; do timeout 120 python tools_op_bench.py all 20 2>&1 | tail -5; done | tee gpurun_out/op_$tag.log
+for rep in 1 2; do timeout 120 python tools/op_bench.py all 20 2>&1 | tail -5; done | tee gpurun_out/op_$tag.log

@@ -1,8 +1,8 @@
 #!/bin/bash
-# GPU box: every -m gpu test (one process per file), smoke(), the bench line. Usage: bash tools_r2_validate.sh <tag>
+# GPU box: every -m gpu test (one process per file), smoke(), the bench line. Usage: bash tools/r2_validate.sh <tag>
 tag=${1:-r2}
 mkdir -p gpurun_out
-bash tools_gpu_check.sh 2>&1 | grep -E "===|passed|failed|rror|e_max|score1|tile 63" | tee gpurun_out/check_$tag.log
+bash tools/gpu_check.sh 2>&1 | grep -E "===|passed|failed|rror|e_max|score1|tile 63" | tee gpurun_out/check_$tag.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke_$tag.txt
 timeout 900 python bench.py 2> gpurun_out/bench_${tag}_err.log > gpurun_out/bench_$tag.json; tail -3 gpurun_out/bench_${tag}_err.log
 python - <<PY

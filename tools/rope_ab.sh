@@ -7,7 +7,7 @@ for rep in 1 2; do
 for U in 0 1; do
   echo "== AIGV_LLM_UNFUSED_ROPE=$U"
   for m in 1_8b 7b; do
-  AIGV_LLM_UNFUSED_ROPE=$U timeout 200 python tools_bench_llm.py $m 2108 1 noref 2>/dev/null | python -c "
+  AIGV_LLM_UNFUSED_ROPE=$U timeout 200 python tools/bench_llm.py $m 2108 1 noref 2>/dev/null | python -c "
 import sys,json
 for l in sys.stdin:
     d=json.loads(l); print(' $m B',d['B'],'ms/prompt',round(d['ms_per_prompt'],3))"

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native kernel (B200_PROFILING.md): tcgen05.mma ->
 UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG/UTMASTG/UTMAREDG/UBLKCP, tcgen05.commit -> UTCBAR, setmaxnreg ->
-USETMAXREG, and the legacy HMMA path (must be 0).   python tools_sass_opcodes.py > profiles/sass_opcodes.txt"""
+USETMAXREG, and the legacy HMMA path (must be 0).   python tools/sass_opcodes.py > profiles/sass_opcodes.txt"""
+import _path  # noqa: F401  (repository root on sys.path)
 import re
 import subprocess
 import sys
